@@ -1,0 +1,248 @@
+// Warp-level (mma.sync m16n8k16) controlled attention. Serves every shape ief_attn_fwd accepts and is the
+// only kernel that can also emit the normalised probabilities (two sweeps: statistics, then P and PV):
+//   AttentionStore self maps, N <= 32^2 (p2p/model/attention_base.py:64-68),
+//   masactrl AttentionStore (masactrl/model/attention_base.py:59-66),
+//   pix2pix-zero attn_probs (pix2pix-zero/model/attention_control.py:46).
+// Same contract as attn_tc.cu: O[b] = softmax(scale Q[q_src[b]] K[k_src[b]]^T) V[v_src[b]], optional second
+// key/value block (MasaCtrl Union, masactrl/model/attention_control.py:100-101).
+#include "mma_utils.cuh"
+#include <math.h>
+
+using namespace mmau;
+
+namespace {
+
+constexpr int kBM = 64, kBN = 64, kThreads = 128;
+constexpr float kLog2e = 1.4426950408889634f;
+
+struct MmaArgs {
+  ief_tensor4 q, k, v, o;
+  int32_t B, H, Nq, Nk, d;
+  int32_t nt1, nt2;
+  float scale_log2;
+  float* probs;         // [B,H,Nq,Nk_total] or null
+  int32_t probs_accum;
+  IefRowTable rows;
+};
+
+template <int DTYPE, int DP, bool WRITE_P>
+__global__ void __launch_bounds__(kThreads)
+attn_mma_kernel(const __grid_constant__ MmaArgs a) {
+  using E = ElemT<DTYPE>;
+  using T = typename E::T;
+  constexpr int LD = DP + 8;
+  constexpr int KS = DP / 16;  // k-steps over head_dim
+  constexpr int NB = DP / 8;   // 8-wide output column blocks
+  const int b = blockIdx.z, h = blockIdx.y, qt = blockIdx.x;
+  if (!a.rows.active[b]) return;
+  extern __shared__ uint4 smem4[];
+  T* sQ = reinterpret_cast<T*>(smem4);
+  T* sK = sQ + kBM * LD;
+  T* sV = sK + kBN * LD;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int nk_total = a.Nk * (a.nt2 > 0 ? 2 : 1);
+
+  const T* qg = reinterpret_cast<const T*>(a.q.ptr) + (int64_t)a.rows.q[b] * a.q.stride_b + (int64_t)h * a.q.stride_h;
+  load_tile<T, kBM, DP, LD, kThreads>(sQ, qg, a.q.stride_n, qt * kBM, a.Nq, a.d, tid);
+  __syncthreads();
+  uint32_t qf[KS][4];
+#pragma unroll
+  for (int kk = 0; kk < KS; ++kk) ldsm_x4(qf[kk], &sQ[(warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LD + kk * 16 + (lane >> 4) * 8]);
+
+  float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f}, inv_l[2] = {1.f, 1.f};
+  float o[NB][4];
+#pragma unroll
+  for (int i = 0; i < NB; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  const float c2 = a.scale_log2;
+  const int nt = a.nt1 + a.nt2;
+  const int grow0 = qt * kBM + warp * 16 + g;  // rows grow0 and grow0 + 8
+
+  constexpr int NSWEEP = WRITE_P ? 2 : 1;
+#pragma unroll 1
+  for (int sweep = 0; sweep < NSWEEP; ++sweep) {
+    const bool stats_only = WRITE_P && sweep == 0;
+    const bool emit = WRITE_P && sweep == 1;
+#pragma unroll 1
+    for (int j = 0; j < nt; ++j) {
+      const bool blk2 = j >= a.nt1;
+      const int jj = blk2 ? j - a.nt1 : j;
+      const int kb = blk2 ? a.rows.k2[b] : a.rows.k[b];
+      const int vb = blk2 ? a.rows.v2[b] : a.rows.v[b];
+      __syncthreads();
+      const T* kg = reinterpret_cast<const T*>(a.k.ptr) + (int64_t)kb * a.k.stride_b + (int64_t)h * a.k.stride_h;
+      load_tile<T, kBN, DP, LD, kThreads>(sK, kg, a.k.stride_n, jj * kBN, a.Nk, a.d, tid);
+      if (!stats_only) {
+        const T* vg = reinterpret_cast<const T*>(a.v.ptr) + (int64_t)vb * a.v.stride_b + (int64_t)h * a.v.stride_h;
+        load_tile<T, kBN, DP, LD, kThreads>(sV, vg, a.v.stride_n, jj * kBN, a.Nk, a.d, tid);
+      }
+      __syncthreads();
+      // S = Q K^T  (16 rows x 64 keys per warp)
+      float s[8][4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < KS; ++kk) {
+#pragma unroll
+        for (int nb2 = 0; nb2 < 4; ++nb2) {
+          uint32_t bf[4];
+          ldsm_x4(bf, &sK[(nb2 * 16 + (lane & 7) + (lane >> 4) * 8) * LD + kk * 16 + ((lane >> 3) & 1) * 8]);
+          mma16816<DTYPE>(s[2 * nb2], qf[kk], bf[0], bf[1]);
+          mma16816<DTYPE>(s[2 * nb2 + 1], qf[kk], bf[2], bf[3]);
+        }
+      }
+      const int vc = min(kBN, a.Nk - jj * kBN);
+      if (vc < kBN) {
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) {
+          const int c = nb * 8 + 2 * t;
+          if (c >= vc) s[nb][0] = s[nb][2] = -INFINITY;
+          if (c + 1 >= vc) s[nb][1] = s[nb][3] = -INFINITY;
+        }
+      }
+      if (!emit) {
+        float tm0 = -INFINITY, tm1 = -INFINITY;
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) {
+          tm0 = fmaxf(tm0, fmaxf(s[nb][0], s[nb][1]));
+          tm1 = fmaxf(tm1, fmaxf(s[nb][2], s[nb][3]));
+        }
+        tm0 = quad_max(tm0);
+        tm1 = quad_max(tm1);
+        const float mn0 = fmaxf(m[0], tm0), mn1 = fmaxf(m[1], tm1);
+        const float al0 = ief_exp2((m[0] - mn0) * c2), al1 = ief_exp2((m[1] - mn1) * c2);
+        m[0] = mn0;
+        m[1] = mn1;
+        l[0] *= al0;
+        l[1] *= al1;
+        if (!stats_only) {
+#pragma unroll
+          for (int i = 0; i < NB; ++i) {
+            o[i][0] *= al0; o[i][1] *= al0; o[i][2] *= al1; o[i][3] *= al1;
+          }
+        }
+      }
+      const float mc0 = m[0] * c2, mc1 = m[1] * c2;
+      float ps0 = 0.f, ps1 = 0.f;
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb) {
+        s[nb][0] = ief_exp2(fmaf(s[nb][0], c2, -mc0)) * inv_l[0];
+        s[nb][1] = ief_exp2(fmaf(s[nb][1], c2, -mc0)) * inv_l[0];
+        s[nb][2] = ief_exp2(fmaf(s[nb][2], c2, -mc1)) * inv_l[1];
+        s[nb][3] = ief_exp2(fmaf(s[nb][3], c2, -mc1)) * inv_l[1];
+        ps0 += s[nb][0] + s[nb][1];
+        ps1 += s[nb][2] + s[nb][3];
+      }
+      if (!emit) { l[0] += ps0; l[1] += ps1; }
+      if (emit && a.rows.pslot[b] >= 0) {
+        // normalised probabilities -> global fp32 (each quad writes one full 32-byte sector per row)
+        const int64_t prow = ((int64_t)a.rows.pslot[b] * a.H + h) * a.Nq;
+        const int col0 = (blk2 ? a.Nk : 0) + jj * kBN;
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) {
+          const int c = nb * 8 + 2 * t;
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int r = grow0 + hh * 8;
+            if (r < a.Nq) {
+              float* dst = a.probs + (prow + r) * nk_total + col0 + c;
+              const float p0 = s[nb][2 * hh], p1 = s[nb][2 * hh + 1];
+              if (c < vc) dst[0] = a.probs_accum ? dst[0] + p0 : p0;
+              if (c + 1 < vc) dst[1] = a.probs_accum ? dst[1] + p1 : p1;
+            }
+          }
+        }
+      }
+      if (!stats_only) {
+        // O += P V
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          uint32_t pa[4];
+          pa[0] = E::pack(s[2 * kk][0], s[2 * kk][1]);
+          pa[1] = E::pack(s[2 * kk][2], s[2 * kk][3]);
+          pa[2] = E::pack(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+          pa[3] = E::pack(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+          for (int nb2 = 0; nb2 < KS; ++nb2) {
+            uint32_t vf[4];
+            ldsm_x4_t(vf, &sV[(kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LD + nb2 * 16 + (lane >> 4) * 8]);
+            mma16816<DTYPE>(o[2 * nb2], pa, vf[0], vf[1]);
+            mma16816<DTYPE>(o[2 * nb2 + 1], pa, vf[2], vf[3]);
+          }
+        }
+      }
+    }
+    if (sweep == 0) {
+      l[0] = quad_sum(l[0]);
+      l[1] = quad_sum(l[1]);
+      if (WRITE_P) { inv_l[0] = 1.f / l[0]; inv_l[1] = 1.f / l[1]; }
+    }
+  }
+  const float f0 = WRITE_P ? 1.f : 1.f / l[0], f1 = WRITE_P ? 1.f : 1.f / l[1];
+  T* og = reinterpret_cast<T*>(a.o.ptr) + (int64_t)b * a.o.stride_b + (int64_t)h * a.o.stride_h;
+#pragma unroll
+  for (int nb = 0; nb < NB; ++nb) {
+    const int c = nb * 8 + 2 * t;
+    if (c < a.d) {
+      if (grow0 < a.Nq) *reinterpret_cast<uint32_t*>(og + (int64_t)grow0 * a.o.stride_n + c) = E::pack(o[nb][0] * f0, o[nb][1] * f0);
+      if (grow0 + 8 < a.Nq) *reinterpret_cast<uint32_t*>(og + (int64_t)(grow0 + 8) * a.o.stride_n + c) = E::pack(o[nb][2] * f1, o[nb][3] * f1);
+    }
+  }
+}
+
+template <int DTYPE, int DP, bool WRITE_P>
+int launch_one(const MmaArgs& a, dim3 grid, cudaStream_t st) {
+  constexpr int smem = (kBM + 2 * kBN) * (DP + 8) * 2;
+  auto kern = attn_mma_kernel<DTYPE, DP, WRITE_P>;
+  static bool configured = false;
+  if (!configured) {
+    IEF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  kern<<<grid, kThreads, smem, st>>>(a);
+  IEF_LAUNCH_OK("attn_mma_kernel");
+  return IEF_OK;
+}
+
+template <int DTYPE, bool WRITE_P>
+int launch_dp(const MmaArgs& a, dim3 grid, cudaStream_t st) {
+  const int d = a.d;
+  if (d <= 32) return launch_one<DTYPE, 32, WRITE_P>(a, grid, st);
+  if (d <= 48) return launch_one<DTYPE, 48, WRITE_P>(a, grid, st);
+  if (d <= 64) return launch_one<DTYPE, 64, WRITE_P>(a, grid, st);
+  if (d <= 80) return launch_one<DTYPE, 80, WRITE_P>(a, grid, st);
+  if (d <= 96) return launch_one<DTYPE, 96, WRITE_P>(a, grid, st);
+  if (d <= 128) return launch_one<DTYPE, 128, WRITE_P>(a, grid, st);
+  return launch_one<DTYPE, 160, WRITE_P>(a, grid, st);
+}
+
+}  // namespace
+
+int ief_attn_mma_launch(const ief_attn_params* p, const IefRowTable& rows, cudaStream_t st) {
+  IEF_REQUIRE(p->dtype == IEF_BF16 || p->dtype == IEF_F16, IEF_ERR_UNSUPPORTED, "ief_attn_fwd: dtype must be bf16 or f16");
+  IEF_REQUIRE(p->d % 8 == 0 && p->d >= 8 && p->d <= 160, IEF_ERR_UNSUPPORTED, "ief_attn_fwd(mma): head_dim %d not a multiple of 8 in [8,160]", p->d);
+  const ief_tensor4* ts[4] = {&p->q, &p->k, &p->v, &p->o};
+  for (auto tt : ts) {
+    IEF_REQUIRE((reinterpret_cast<uintptr_t>(tt->ptr) & 15) == 0, IEF_ERR_INVALID, "ief_attn_fwd: pointer not 16-byte aligned");
+    IEF_REQUIRE(tt->stride_n % 8 == 0 && tt->stride_h % 8 == 0 && tt->stride_b % 8 == 0, IEF_ERR_UNSUPPORTED,
+                "ief_attn_fwd: strides must be multiples of 8 elements");
+  }
+  MmaArgs a;
+  a.q = p->q; a.k = p->k; a.v = p->v; a.o = p->o;
+  a.B = p->B; a.H = p->H; a.Nq = p->Nq; a.Nk = p->Nk; a.d = p->d;
+  a.nt1 = ief_ceil_div(p->Nk, kBN);
+  bool any2 = false;
+  for (int i = 0; i < p->B; ++i) any2 |= rows.k2[i] >= 0;
+  if (any2)
+    for (int i = 0; i < p->B; ++i)
+      IEF_REQUIRE(rows.k2[i] >= 0 && rows.v2[i] >= 0, IEF_ERR_UNSUPPORTED, "k_src2/v_src2 must be set for every row or none");
+  a.nt2 = any2 ? a.nt1 : 0;
+  a.scale_log2 = p->scale * kLog2e;
+  a.probs = p->probs_out;
+  a.probs_accum = p->probs_accum;
+  a.rows = rows;
+  dim3 grid(ief_ceil_div(p->Nq, kBM), p->H, p->B);
+  if (p->probs_out) {
+    return p->dtype == IEF_BF16 ? launch_dp<IEF_BF16, true>(a, grid, st) : launch_dp<IEF_F16, true>(a, grid, st);
+  }
+  return p->dtype == IEF_BF16 ? launch_dp<IEF_BF16, false>(a, grid, st) : launch_dp<IEF_F16, false>(a, grid, st);
+}

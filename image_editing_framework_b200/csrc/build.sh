@@ -1,0 +1,18 @@
+#!/usr/bin/env bash
+# Builds libief_b200.so (sm_100a only) in-tree. Usage: build.sh [out_dir]
+set -euo pipefail
+here="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+out="${1:-$here/..}"
+NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
+FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr)
+objs=()
+pids=()
+mkdir -p "$here/build"
+for f in api attn_tc attn_mma cross_attn elementwise; do
+  "$NVCC" "${FLAGS[@]}" -c "$here/$f.cu" -o "$here/build/$f.o" &
+  pids+=($!)
+  objs+=("$here/build/$f.o")
+done
+for p in "${pids[@]}"; do wait "$p"; done
+"$NVCC" -shared -o "$out/libief_b200.so" "${objs[@]}" -lcudart_static -ldl -lrt -lpthread
+echo "built $out/libief_b200.so"

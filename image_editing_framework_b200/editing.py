@@ -1,0 +1,84 @@
+"""Compact L4 drivers (the 50-step denoise loops of the reference's `*/model/sd_utils.py`) wired to the fused step.
+
+These mirror the reference call sequences so end-to-end parity tests and bench.py can run a whole edit:
+  p2p_edit       p2p/model/sd_utils.py:24-79        (register -> loop: unet(cat[latents]*2) -> CFG -> scheduler.step -> step_callback)
+  masactrl_edit  masactrl/model/sd_utils.py:25-124
+  pnp_edit       pnp/model/sd_utils.py:23-115       (register_time per step, q/k + feature injection schedules)
+Orchestration only — every attention call goes through the registered closures, every step update through FusedDDIM.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+
+from .ddim import FusedDDIM
+from .p2p.register import register_attention_control
+from .pnp import register as pnp_register
+
+
+def encode_prompts(model, prompts: List[str]) -> torch.Tensor:
+    """[uncond * n, cond * n] context, as every reference driver builds it."""
+    tok = model.tokenizer(prompts, padding="max_length", max_length=model.tokenizer.model_max_length, truncation=True, return_tensors="pt")
+    cond = model.text_encoder(tok.input_ids.to(model.device))[0]
+    un = model.tokenizer([""] * len(prompts), padding="max_length", max_length=tok.input_ids.shape[-1], return_tensors="pt")
+    uncond = model.text_encoder(un.input_ids.to(model.device))[0]
+    return torch.cat([uncond, cond])
+
+
+@torch.no_grad()
+def denoise(model, latents: torch.Tensor, context: torch.Tensor, num_inference_steps: int, guidance_scale: float,
+            step_callback=None, per_step=None) -> torch.Tensor:
+    model.scheduler.set_timesteps(num_inference_steps)
+    fused = FusedDDIM(model.scheduler)
+    for t in model.scheduler.timesteps.tolist():
+        if per_step is not None:
+            per_step(t)
+        noise_pred = model.unet(torch.cat([latents] * 2), t, encoder_hidden_states=context)["sample"]
+        latents = fused.step(noise_pred, t, latents, guidance_scale)
+        if step_callback is not None:
+            latents = step_callback(latents)
+    return latents
+
+
+@torch.no_grad()
+def p2p_edit(model, prompts: List[str], controller, latent: torch.Tensor, num_inference_steps: int = 50, guidance_scale: float = 7.5,
+             context: Optional[torch.Tensor] = None) -> torch.Tensor:
+    if controller is not None:
+        register_attention_control(model, controller)
+    context = encode_prompts(model, prompts) if context is None else context
+    latents = (latent * model.scheduler.init_noise_sigma).expand(len(prompts), *latent.shape[1:]).contiguous()
+    return denoise(model, latents, context, num_inference_steps, guidance_scale,
+                   step_callback=controller.step_callback if controller is not None else None)
+
+
+@torch.no_grad()
+def masactrl_edit(model, prompts: List[str], latents: torch.Tensor, num_inference_steps: int = 50, guidance_scale: float = 7.5,
+                  context: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """The editor must already be registered (masactrl/edit_real.py:137-138)."""
+    context = encode_prompts(model, prompts) if context is None else context
+    return denoise(model, latents, context, num_inference_steps, guidance_scale)
+
+
+@torch.no_grad()
+def pnp_edit(model, prompts: List[str], latents: torch.Tensor, num_inference_steps: int = 50, guidance_scale: float = 7.5,
+             pnp_attn_t: float = 0.5, pnp_f_t: float = 0.8, context: Optional[torch.Tensor] = None, xl: bool = False) -> torch.Tensor:
+    model.scheduler.set_timesteps(num_inference_steps)
+    ts = model.scheduler.timesteps
+    qk_t, f_t = int(num_inference_steps * pnp_attn_t), int(num_inference_steps * pnp_f_t)
+    qk_sched = ts[:qk_t] if qk_t >= 0 else []
+    conv_sched = ts[:f_t] if f_t >= 0 else []
+    reg = (pnp_register.register_attention_control_efficient_xl, pnp_register.register_conv_control_efficient_xl,
+           pnp_register.register_time_xl, pnp_register.unregister_attention_control_efficient_xl,
+           pnp_register.unregister_conv_control_efficient_xl) if xl else (
+        pnp_register.register_attention_control_efficient, pnp_register.register_conv_control_efficient,
+        pnp_register.register_time, pnp_register.unregister_attention_control_efficient,
+        pnp_register.unregister_conv_control_efficient)
+    reg[0](model, qk_sched)
+    reg[1](model, conv_sched)
+    context = encode_prompts(model, prompts) if context is None else context
+    try:
+        return denoise(model, latents, context, num_inference_steps, guidance_scale, per_step=lambda t: reg[2](model, t))
+    finally:
+        reg[3](model)
+        reg[4](model)

@@ -1,0 +1,5 @@
+from .register import register_attention_control, unregister_attention_control
+from .attention_base import AttentionControl, EmptyControl, AttentionStore, AttentionControlEdit
+from .attention_control import AttentionReplace, AttentionRefine, AttentionReweight
+from .ptp_utils import LocalBlend, get_time_words_attention_alpha
+from . import seq_aligner

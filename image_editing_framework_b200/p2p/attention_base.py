@@ -1,0 +1,228 @@
+"""Prompt-to-Prompt controllers — same classes, constructors and public state as p2p/model/attention_base.py,
+but each layer call is ONE fused kernel instead of "materialise softmax(QK^T), edit it, bmm".
+
+Reference                                    here
+  AttentionControl.__call__ :16-28            AttentionControl.attend(): same gating on cur_att_layer / LOW_RESOURCE,
+                                              same counter arithmetic (_tick), cond-half-only editing
+  AttentionStore :57-91                       maps written by the attention kernels' epilogues straight into
+                                              `attention_store` (overwrite on the first step, += afterwards): there is
+                                              no step_store and no python `+=` loop
+  AttentionControlEdit.forward :113-125       per-row source indices (self) / ief_cross_attn_edit_fwd tables (cross)
+  replace_self_attention :132-136             rows 1.. of the cond half read Q,K of the base row when N <= 16^2
+
+The counters are advanced exactly like the reference so `cur_step` / `cur_att_layer` stay drop-in observable.
+"""
+from __future__ import annotations
+
+import abc
+from typing import Dict, List, Optional, Tuple, Union
+
+import torch
+
+from .. import ops
+from . import ptp_utils
+from .ptp_utils import LocalBlend
+
+_STORE_MAX_TOKENS = 32 ** 2   # reference :66 "avoid memory overhead"
+_SELF_REPLACE_MAX_TOKENS = 16 ** 2  # reference :133
+
+
+class AttentionControl(abc.ABC):
+
+    def __init__(self, LOW_RESOURCE):
+        self.cur_step = 0
+        self.num_att_layers = -1
+        self.cur_att_layer = 0
+        self.LOW_RESOURCE = LOW_RESOURCE
+
+    # ---- counters (reference :16-28) ---------------------------------------------------------------------------
+    @property
+    def num_uncond_att_layers(self):
+        return self.num_att_layers if self.LOW_RESOURCE else 0
+
+    def _tick(self) -> None:
+        self.cur_att_layer += 1
+        if self.cur_att_layer == self.num_att_layers + self.num_uncond_att_layers:
+            self.cur_att_layer = 0
+            self.cur_step += 1
+            self.between_steps()
+
+    def _edited_rows(self, batch: int) -> Tuple[int, int]:
+        """[first, last) UNet batch rows the controller acts on: everything in LOW_RESOURCE's cond pass,
+        else the cond half `attn[h // 2:]` (reference :20-22)."""
+        return (0, batch) if self.LOW_RESOURCE else (batch // 2, batch)
+
+    # ---- fused entry point used by register_attention_control ---------------------------------------------------
+    def attend(self, q, k, v, heads: int, scale: float, is_cross: bool, place_in_unet: str) -> torch.Tensor:
+        """Equivalent of `bmm(self(softmax(scale q k^T), is_cross, place_in_unet), v)` on [B, N, H*d] projections."""
+        if self.cur_att_layer >= self.num_uncond_att_layers:
+            out = self.fused_forward(q, k, v, heads, scale, is_cross, place_in_unet)
+        else:
+            out = _plain(q, k, v, heads, scale, is_cross)
+        self._tick()
+        return out
+
+    @abc.abstractmethod
+    def fused_forward(self, q, k, v, heads, scale, is_cross: bool, place_in_unet: str) -> torch.Tensor:
+        raise NotImplementedError
+
+    # ---- reference API that has no fused meaning -----------------------------------------------------------------
+    def __call__(self, attn, is_cross: bool, place_in_unet: str):
+        raise RuntimeError(
+            f"{type(self).__name__}: the materialised-probability entry point controller(attn, is_cross, place) is not served by "
+            "the fused path (no N x N probability tensor exists). Install the controller with register_attention_control; a "
+            "custom controller must implement fused_forward().")
+
+    def forward(self, attn, is_cross: bool, place_in_unet: str):
+        return self.__call__(attn, is_cross, place_in_unet)
+
+    def step_callback(self, x_t):
+        return x_t
+
+    def between_steps(self):
+        return None
+
+    def reset(self):
+        self.cur_step = 0
+        self.cur_att_layer = 0
+
+
+def _plain(q, k, v, heads, scale, is_cross):
+    if is_cross and k.shape[1] <= 80:
+        return ops.cross_attention_edit(q, k, v, heads, scale)
+    return ops.attention(q, k, v, heads, scale)
+
+
+class EmptyControl(AttentionControl):
+
+    def __init__(self, LOW_RESOURCE):
+        super().__init__(LOW_RESOURCE)
+
+    def fused_forward(self, q, k, v, heads, scale, is_cross, place_in_unet):
+        return _plain(q, k, v, heads, scale, is_cross)
+
+
+class AttentionStore(AttentionControl):
+    """`attention_store[key][i]` holds the SUM over finished steps of the cond-half maps of the i-th stored layer of
+    that key, shape [rows*heads, N, M] fp32 — the tensors the reference ends up with (:67 alias + :81 `+=`)."""
+
+    def __init__(self, LOW_RESOURCE):
+        super().__init__(LOW_RESOURCE)
+        self.step_store = self.get_empty_store()  # kept for API parity; the fused epilogue writes the store directly
+        self.attention_store: Dict[str, List[torch.Tensor]] = {}
+        self._slot = self._zero_slots()
+        self._store_enabled = True
+
+    @staticmethod
+    def get_empty_store():
+        return {"down_cross": [], "mid_cross": [], "up_cross": [], "down_self": [], "mid_self": [], "up_self": []}
+
+    @staticmethod
+    def _zero_slots():
+        return {"down_cross": 0, "mid_cross": 0, "up_cross": 0, "down_self": 0, "mid_self": 0, "up_self": 0}
+
+    def _store_target(self, key: str, rows: int, heads: int, n: int, m: int, device) -> Tuple[torch.Tensor, bool]:
+        """Buffer for this layer's maps and whether the kernel must accumulate into it (every step but the first)."""
+        if len(self.attention_store) == 0:
+            self.attention_store = self.get_empty_store()
+        bufs = self.attention_store[key]
+        i = self._slot[key]
+        self._slot[key] = i + 1
+        if i == len(bufs):
+            bufs.append(torch.empty((rows * heads, n, m), dtype=torch.float32, device=device))
+            return bufs[i], False
+        return bufs[i], True
+
+    def _stores(self, n_tokens: int) -> bool:
+        return self._store_enabled and n_tokens <= _STORE_MAX_TOKENS
+
+    def fused_forward(self, q, k, v, heads, scale, is_cross, place_in_unet):
+        return self._attend_and_store(q, k, v, heads, scale, is_cross, place_in_unet)
+
+    def _attend_and_store(self, q, k, v, heads, scale, is_cross, place_in_unet, *, self_src=None, cross_kw=None):
+        B, N, M = q.shape[0], q.shape[1], k.shape[1]
+        lo, hi = self._edited_rows(B)
+        probs = accum = slots = None
+        if self._stores(N):
+            key = f"{place_in_unet}_{'cross' if is_cross else 'self'}"
+            probs, accum = self._store_target(key, hi - lo, heads, N, M, q.device)
+            slots = [(b - lo) if lo <= b < hi else -1 for b in range(B)]
+        if is_cross:
+            if M > 80:
+                raise NotImplementedError(f"cross-attention with {M} keys: the fused edit kernel holds at most 80")
+            return ops.cross_attention_edit(q, k, v, heads, scale, probs_out=probs, probs_accum=bool(accum), store_slot=slots,
+                                            **(cross_kw or {}))
+        return ops.attention(q, k, v, heads, scale, probs_out=probs, probs_accum=bool(accum), probs_slot=slots, **(self_src or {}))
+
+    def between_steps(self):
+        self._slot = self._zero_slots()
+
+    def get_average_attention(self):
+        return {key: [item / self.cur_step for item in self.attention_store[key]] for key in self.attention_store}
+
+    def reset(self):
+        super().reset()
+        self.step_store = self.get_empty_store()
+        self.attention_store = {}
+        self._slot = self._zero_slots()
+
+
+class AttentionControlEdit(AttentionStore, abc.ABC):
+    """As shipped, the reference derives this class from AttentionControl only, so `local_blend` crashes on the missing
+    `attention_store`. Here it derives from AttentionStore the way upstream Prompt-to-Prompt does;
+    maps are only stored when a LocalBlend needs them, so without one the behaviour (and memory) is the reference's."""
+
+    def __init__(self, prompts, tokenizer, num_steps: int,
+                 cross_replace_steps: Union[float, Tuple[float, float], Dict[str, Tuple[float, float]]],
+                 self_replace_steps: Union[float, Tuple[float, float]],
+                 local_blend: Optional[LocalBlend], device=torch.device("cuda:0"), LOW_RESOURCE=False):
+        super().__init__(LOW_RESOURCE)
+        self.batch_size = len(prompts)
+        self.cross_replace_alpha = ptp_utils.get_time_words_attention_alpha(prompts, num_steps, cross_replace_steps, tokenizer).to(device)
+        if type(self_replace_steps) is float:
+            self_replace_steps = 0, self_replace_steps
+        self.num_self_replace = int(num_steps * self_replace_steps[0]), int(num_steps * self_replace_steps[1])
+        self.local_blend = local_blend
+        self._store_enabled = local_blend is not None
+        self._device = torch.device(device)
+        # [num_steps+1, n_targets, 77] fp32 contiguous: row `cur_step` is handed to the kernel as-is
+        self._alpha_table = self.cross_replace_alpha.reshape(num_steps + 1, self.batch_size - 1, -1).to(torch.float32).contiguous()
+        self._edit: Optional[ops.CrossEdit] = None
+
+    @abc.abstractmethod
+    def cross_edit(self) -> ops.CrossEdit:
+        """Device tables describing replace_cross_attention for the fused kernel."""
+        raise NotImplementedError
+
+    def replace_cross_attention(self, attn_base, att_replace):
+        raise RuntimeError("replace_cross_attention on materialised maps is folded into ief_cross_attn_edit_fwd; see cross_edit()")
+
+    def _row_tables(self, batch: int):
+        lo, hi = self._edited_rows(batch)
+        if hi - lo != self.batch_size:
+            raise ValueError(f"controller was built for {self.batch_size} prompts but the edited half of the UNet batch has {hi - lo} rows")
+        base = [-1] * batch
+        slot = [0] * batch
+        for i in range(1, self.batch_size):
+            base[lo + i], slot[lo + i] = lo, i - 1
+        return lo, base, slot
+
+    def fused_forward(self, q, k, v, heads, scale, is_cross, place_in_unet):
+        B, N = q.shape[0], q.shape[1]
+        if is_cross:
+            if self._edit is None:
+                self._edit = self.cross_edit()
+            _, base, slot = self._row_tables(B)
+            kw = dict(edit=self._edit, step_alpha=self._alpha_table[self.cur_step], base_row=base, edit_slot=slot)
+            return self._attend_and_store(q, k, v, heads, scale, True, place_in_unet, cross_kw=kw)
+        src = None
+        if self.num_self_replace[0] <= self.cur_step < self.num_self_replace[1] and N <= _SELF_REPLACE_MAX_TOKENS:
+            lo, base, _ = self._row_tables(B)
+            qk = [base[b] if base[b] >= 0 else b for b in range(B)]
+            src = dict(q_src=qk, k_src=qk)  # probabilities of the base prompt, values of the row itself
+        return self._attend_and_store(q, k, v, heads, scale, False, place_in_unet, self_src=src)
+
+    def step_callback(self, x_t):
+        if self.local_blend is not None:
+            x_t = self.local_blend(x_t, self.attention_store)
+        return x_t
