@@ -1,0 +1,273 @@
+"""Generate the committed golden fixtures by running the REFERENCE's own Python (read-only, /root/reference)
+on the stand-in pipeline, CPU fp32, fixed seeds.  Run in the build container only:
+
+    python tests/golden/make_goldens.py
+
+The reference ships no tests or golden vectors, so these files are what pins the oracle
+(oracle/controlled_attention.py) and the product's host-side integer code (seq_aligner / ptp_utils).
+Everything a test needs to rebuild the inputs (config, seeds, prompts) is stored next to the outputs.
+Compositions the reference cannot execute as shipped (AttentionStore + edit, LocalBlend — SURVEY.md facts 0.5-0.7)
+are generated from the reference classes re-composed the upstream Prompt-to-Prompt way and are labelled "recomposed".
+"""
+import os
+import sys
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle.reference_loader import load_reference  # noqa: E402
+from image_editing_framework_b200.standin import make_pipeline, tiny_config, WordPieceTokenizer, DDIMScheduler  # noqa: E402
+from image_editing_framework_b200.standin.unet import UNetConfig  # noqa: E402
+
+CPU = torch.device("cpu")
+
+PROMPT_CASES = [
+    # (source, target, kind)
+    ("a photo of a cat sitting on a bench", "a photo of a dog sitting on a bench", "replace"),
+    ("a squirrel eating a burger", "a lion eating a burger", "replace"),            # 3-token word -> 1-token word: ratio branch
+    ("a cat on a table", "a hippopotamus on a table", "replace"),                   # 1 token -> 3 tokens
+    ("a painting of a house", "a watercolor painting of a large house by the lake", "refine"),
+    ("a bowl of soup", "a bowl of pea soup", "refine"),
+    ("children playing near the river at sunset", "children near the frozen river", "refine"),  # deletions and insertions
+    ("a", "a", "replace"),
+]
+
+
+def _save(name, obj):
+    path = os.path.join(HERE, name)
+    torch.save(obj, path)
+    print(f"wrote {name}: {os.path.getsize(path) / 1024:.1f} KiB")
+
+
+# ------------------------------------------------------------------------------------------------ host-side integer code
+def gen_aligner():
+    ref = load_reference("p2p")
+    tok = WordPieceTokenizer()
+    cases = []
+    for src, tgt, kind in PROMPT_CASES:
+        c = dict(source=src, target=tgt, kind=kind, src_ids=tok.encode(src), tgt_ids=tok.encode(tgt))
+        if kind == "replace":
+            c["replacement_mapper"] = ref.seq_aligner.get_replacement_mapper([src, tgt], tok)
+        c["refinement_mapper"], c["refinement_alphas"] = ref.seq_aligner.get_refinement_mapper([src, tgt], tok)
+        words = tgt.split(" ")
+        c["word_inds"] = {w: ref.seq_aligner.get_word_inds(tgt, w, tok).tolist() for w in set(words)}
+        c["word_inds_by_pos"] = [ref.seq_aligner.get_word_inds(tgt, i, tok).tolist() for i in range(len(words))]
+        c["equalizer"] = ref.seq_aligner.get_equalizer(tok, tgt, (words[-1],), (2.0,))
+        c["alpha_float"] = ref.ptp_utils.get_time_words_attention_alpha([src, tgt], 10, 0.8, tok)
+        c["alpha_dict"] = ref.ptp_utils.get_time_words_attention_alpha([src, tgt], 10, {"default_": 1.0, words[-1]: (0.2, 0.6)}, tok)
+        cases.append(c)
+    multi = ["a photo of a cat", "a photo of a dog", "a photo of a fox"]
+    extra = dict(prompts=multi, replacement=ref.seq_aligner.get_replacement_mapper(multi, tok),
+                 refinement=ref.seq_aligner.get_refinement_mapper(multi, tok),
+                 alpha=ref.ptp_utils.get_time_words_attention_alpha(multi, 50, (0.1, 0.7), tok))
+    _save("aligner.pt", dict(cases=cases, multi=extra))
+
+
+# ------------------------------------------------------------------------------------------------ per-layer recording
+class Recorder:
+    """Wraps the forward of every patched Attention so that each call's output is recorded in call order."""
+
+    def __init__(self, unet, steps_to_keep):
+        self.keep, self.step, self.records = set(steps_to_keep), 0, {}
+        self.mods = [m for m in unet.modules() if type(m).__name__ == "Attention"]
+        for m in self.mods:
+            inner = m.forward
+            m.forward = self._wrap(inner)
+
+    def _wrap(self, inner):
+        def fwd(*a, **kw):
+            out = inner(*a, **kw)
+            if self.step in self.keep:
+                self.records.setdefault(self.step, []).append(out.detach().clone())
+            return out
+        return fwd
+
+
+def _latent(seed, shape):
+    return torch.randn(shape, generator=torch.Generator().manual_seed(seed))
+
+
+def gen_p2p():
+    ref = load_reference("p2p")
+    out = {}
+    steps, keep = 5, (1, 4)
+    for name, kind in (("replace", "replace"), ("refine", "refine"), ("reweight", "reweight"), ("store", "store"), ("empty", "empty")):
+        pipe = make_pipeline(tiny_config(), seed=0)
+        src, tgt = ("a photo of a cat sitting on a bench", "a photo of a dog sitting on a bench") if kind != "refine" else \
+                   ("a bowl of soup", "a bowl of pea soup")
+        prompts = [src, tgt]
+        common = dict(prompts=prompts, tokenizer=pipe.tokenizer, num_steps=steps, cross_replace_steps=0.8, self_replace_steps=0.6, device=CPU)
+        if kind == "replace":
+            ctrl = ref.attention_control.AttentionReplace(**common)
+        elif kind == "refine":
+            ctrl = ref.attention_control.AttentionRefine(**common)
+        elif kind == "reweight":
+            eq = ref.seq_aligner.get_equalizer(pipe.tokenizer, tgt, ("dog",), (3.0,))
+            prev = ref.attention_control.AttentionReplace(**common)
+            ctrl = ref.attention_control.AttentionReweight(equalizer=eq, controller=prev, **common)
+        elif kind == "store":
+            ctrl = ref.attention_base.AttentionStore(False)
+        else:
+            ctrl = ref.attention_base.EmptyControl(False)
+        editor = ref.sd_utils.P2P(pipe, steps)
+        ref.register.register_attention_control(pipe, ctrl)
+        rec = Recorder(pipe.unet, keep)
+        context = _context(pipe, prompts)
+        latent = _latent(1, (1, 4, 16, 16))
+        latents = latent.expand(2, 4, 16, 16)
+        per_step = []
+        with torch.no_grad():
+            for i, t in enumerate(pipe.scheduler.timesteps):
+                rec.step = i
+                latents = editor.diffusion_step(pipe, ctrl, latents, context, t, 7.5, False)
+                per_step.append(latents.clone())
+        g = dict(prompts=prompts, steps=steps, keep=keep, latent_seed=1, pipe_seed=0, guidance=7.5, layer_outputs=rec.records,
+                 latents_per_step=per_step, num_att_layers=ctrl.num_att_layers, cur_step=ctrl.cur_step)
+        if kind == "store":
+            avg = ctrl.get_average_attention()
+            g["average_attention"] = {k: [t.clone() for t in v] for k, v in avg.items()}
+        out[name] = g
+    _save("p2p.pt", out)
+
+
+def _context(pipe, prompts):
+    tok = pipe.tokenizer(prompts, padding="max_length", max_length=77, truncation=True, return_tensors="pt")
+    cond = pipe.text_encoder(tok.input_ids)[0]
+    un = pipe.tokenizer([""] * len(prompts), padding="max_length", max_length=77, return_tensors="pt")
+    return torch.cat([pipe.text_encoder(un.input_ids)[0], cond])
+
+
+def gen_p2p_localblend():
+    """RECOMPOSED oracle: AttentionReplace + AttentionStore + LocalBlend the upstream way (the reference classes crash as
+    shipped). 64x64 latents so that the stored maps LocalBlend reads are 16x16."""
+    ref = load_reference("p2p")
+    AB, AC = ref.attention_base, ref.attention_control
+
+    class ReplaceWithStore(AC.AttentionReplace):
+        def __init__(self, *a, **kw):
+            super().__init__(*a, **kw)
+            self.step_store = AB.AttentionStore.get_empty_store()
+            self.attention_store = {}
+
+        def forward(self, attn, is_cross, place_in_unet):
+            AB.AttentionStore.forward(self, attn, is_cross, place_in_unet)
+            return super().forward(attn, is_cross, place_in_unet)
+
+        between_steps = AB.AttentionStore.between_steps
+
+    cfg = UNetConfig(sample_size=64, block_out_channels=(16, 32, 32, 32), num_heads=(2, 2, 2, 2), cross_attention_dim=32, norm_num_groups=8, name="tiny64")
+    pipe = make_pipeline(cfg, seed=3)
+    prompts = ["a photo of a cat sitting on a bench", "a photo of a dog sitting on a bench"]
+    steps = 3
+    lb = ref.ptp_utils.LocalBlend(pipe.tokenizer, prompts, [["cat"], ["dog"]], device=CPU)
+    ctrl = ReplaceWithStore(prompts, pipe.tokenizer, steps, 0.8, 0.6, lb, device=CPU)
+    editor = ref.sd_utils.P2P(pipe, steps)
+    ref.register.register_attention_control(pipe, ctrl)
+    context = _context(pipe, prompts)
+    latents = _latent(5, (1, 4, 64, 64)).expand(2, 4, 64, 64)
+    per_step = []
+    with torch.no_grad():
+        for t in pipe.scheduler.timesteps:
+            latents = editor.diffusion_step(pipe, ctrl, latents, context, t, 7.5, False)
+            per_step.append(latents.clone())
+    maps = ctrl.attention_store["down_cross"][2:4] + ctrl.attention_store["up_cross"][:3]
+    _save("p2p_localblend.pt", dict(recomposed=True, prompts=prompts, steps=steps, latent_seed=5, pipe_seed=3, guidance=7.5,
+                                    config=cfg, blend_words=[["cat"], ["dog"]], latents_per_step=per_step,
+                                    store_16=[m.clone() for m in maps]))
+    # stand-alone LocalBlend known-answer on synthetic maps
+    g = torch.Generator().manual_seed(8)
+    syn = [torch.rand(16, 256, 77, generator=g) ** 4 for _ in range(5)]
+    x = torch.randn(2, 4, 64, 64, generator=g)
+    store = {"down_cross": [None, None, syn[0], syn[1]], "up_cross": syn[2:]}
+    _save("local_blend.pt", dict(seed=8, x_out=lb(x, store), alpha_layers=lb.alpha_layers.clone()))
+
+
+def gen_masactrl():
+    ref = load_reference("masactrl")
+    pipe = make_pipeline(tiny_config(), seed=1)
+    steps, keep = 4, (0, 2)
+    prompts = ["a photo of a sitting cat", "a photo of a running cat"]
+    editor = ref.sd_utils.MasaCtrl(pipe, steps)
+    ctrl = ref.attention_control.MutualSelfAttentionControl(1, 10, total_steps=steps)
+    ref.register.regiter_attention_editor_diffusers(pipe, ctrl)
+    rec = Recorder(pipe.unet, keep)
+    context = _context(pipe, prompts)
+    init = _latent(2, (1, 4, 16, 16))
+    latents = torch.cat([init, init])
+    per_step = []
+    with torch.no_grad():
+        for i, t in enumerate(pipe.scheduler.timesteps):
+            rec.step = i
+            noise = pipe.unet(torch.cat([latents] * 2), t, encoder_hidden_states=context).sample
+            nu, nc = noise.chunk(2, dim=0)
+            latents = pipe.scheduler.step(nu + 7.5 * (nc - nu), t, latents, return_dict=True)["prev_sample"]  # sd_utils.py:107-113
+            per_step.append(latents.clone())
+    _save("masactrl.pt", dict(prompts=prompts, steps=steps, keep=keep, latent_seed=2, pipe_seed=1, guidance=7.5, start_step=1, start_layer=10,
+                              layer_outputs=rec.records, latents_per_step=per_step, num_att_layers=ctrl.num_att_layers))
+
+
+def gen_pnp():
+    ref = load_reference("pnp")
+    pipe = make_pipeline(tiny_config(), seed=2)
+    steps, keep = 4, (0, 3)
+    prompts = ["a photo of a wooden horse", "a photo of a bronze horse"]
+    pipe.scheduler.set_timesteps(steps)
+    ts = pipe.scheduler.timesteps
+    qk_t, f_t = int(steps * 0.5), int(steps * 0.8)
+    ref.register.register_attention_control_efficient(pipe, ts[:qk_t])
+    ref.register.register_conv_control_efficient(pipe, ts[:f_t])
+    rec = Recorder(pipe.unet, keep)
+    context = _context(pipe, prompts)
+    init = _latent(3, (1, 4, 16, 16))
+    latents = torch.cat([init, init])
+    per_step = []
+    with torch.no_grad():
+        for i, t in enumerate(ts):
+            rec.step = i
+            ref.register.register_time(pipe, t.item())
+            noise = pipe.unet(torch.cat([latents] * 2), t, encoder_hidden_states=context).sample
+            nu, nc = noise.chunk(2)
+            latents = pipe.scheduler.step(nu + 7.5 * (nc - nu), t, latents).prev_sample      # pnp/model/sd_utils.py:99-107
+            per_step.append(latents.clone())
+    _save("pnp.pt", dict(prompts=prompts, steps=steps, keep=keep, latent_seed=3, pipe_seed=2, guidance=7.5, pnp_attn_t=0.5, pnp_f_t=0.8,
+                         layer_outputs=rec.records, latents_per_step=per_step))
+
+
+def gen_pix2pix_zero():
+    ref = load_reference("pix2pix-zero")
+    pipe = make_pipeline(tiny_config(), seed=4)
+    unet, _ = ref.attention_control.prep_unet(pipe.unet)
+    rec = Recorder(unet, (0,))
+    prompts = ["a photo of a cat"]
+    context = _context(pipe, prompts)
+    x = _latent(4, (1, 4, 16, 16))
+    with torch.no_grad():
+        out = unet(torch.cat([x] * 2), torch.tensor(981), encoder_hidden_states=context).sample
+    probs = {name: m.attn_probs.clone() for name, m in unet.named_modules() if type(m).__name__ == "Attention" and "attn2" in name}
+    _save("pix2pix_zero.pt", dict(prompts=prompts, latent_seed=4, pipe_seed=4, t=981, unet_out=out, layer_outputs=rec.records[0], cross_probs=probs))
+
+
+def gen_ddim():
+    ref = load_reference("p2p")
+    from types import SimpleNamespace
+    sch = DDIMScheduler()
+    sch.set_timesteps(50)
+    model = SimpleNamespace(scheduler=sch)
+    inv = ref.ddim.ddim_inversion()
+    g = torch.Generator().manual_seed(6)
+    eps, x = torch.randn(1, 4, 64, 64, generator=g), torch.randn(1, 4, 64, 64, generator=g)
+    rev = {int(t): inv.ddim_reverse(model, eps, torch.tensor(int(t)), x) for t in (1, 21, 501, 981)}
+    eu, ec = torch.randn(2, 4, 64, 64, generator=g), torch.randn(2, 4, 64, 64, generator=g)
+    xx = torch.randn(2, 4, 64, 64, generator=g)
+    fwd = {int(t): sch.step(eu + 7.5 * (ec - eu), int(t), xx)["prev_sample"] for t in (981, 501, 21, 1)}
+    _save("ddim.pt", dict(seed=6, reverse=rev, forward=fwd, guidance=7.5, timesteps=sch.timesteps.clone(), alphas_cumprod=sch.alphas_cumprod.clone()))
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(8)
+    which = sys.argv[1:] or ["aligner", "ddim", "p2p", "masactrl", "pnp", "pix2pix_zero", "p2p_localblend"]
+    for w in which:
+        globals()["gen_" + w]()

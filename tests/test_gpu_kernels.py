@@ -1,0 +1,280 @@
+"""Parity of every CUDA kernel (called through the C ABI) against the CPU oracle on seeded inputs.
+
+Tolerance: north_star states 2e-2 max-abs for bf16/fp16 attention outputs relative to the fp32 reference; integer /
+fp32-elementwise work (DDIM step, store accumulate) is checked bit-exact.
+"""
+import math
+
+import pytest
+import torch
+
+from image_editing_framework_b200 import ops, _cabi
+from oracle import controlled_attention as orc
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-2
+
+
+def _qkv(B, N, M, H, d, seed, dtype=torch.bfloat16, spread=1.0):
+    g = torch.Generator().manual_seed(seed)
+    q = (torch.randn(B, N, H * d, generator=g) * spread).to(dtype)
+    k = (torch.randn(B, M, H * d, generator=g) * spread).to(dtype)
+    v = torch.randn(B, M, H * d, generator=g).to(dtype)
+    return q, k, v
+
+
+# ---------------------------------------------------------------------------------------------------- UMMA probe
+@pytest.mark.parametrize("N,K,b_mn,a_tmem", [
+    (128, 64, False, False), (128, 48, False, False), (128, 128, False, False), (64, 16, False, False),
+    (64, 128, True, False), (48, 128, True, False), (64, 128, True, True), (48, 128, True, True),
+    (80, 128, True, True), (128, 128, True, True), (160, 128, True, True), (192, 64, True, True),
+])
+def test_umma_probe(cuda, N, K, b_mn, a_tmem):
+    g = torch.Generator().manual_seed(N * 1000 + K)
+    a = torch.randn(128, K, generator=g).to(torch.bfloat16)
+    b = (torch.randn(K, N, generator=g) if b_mn else torch.randn(N, K, generator=g)).to(torch.bfloat16)
+    want = a.float() @ (b.float() if b_mn else b.float().t())
+    got = ops.umma_probe(a.to(cuda), b.to(cuda), b_mn, a_tmem).cpu()
+    torch.cuda.synchronize()
+    assert torch.allclose(got, want, atol=1e-2, rtol=1e-3), f"max err {(got - want).abs().max().item()}"
+
+
+# ---------------------------------------------------------------------------------------------------- self attention
+SHAPES_MMA = [  # B, H, Nq, Nk, d
+    (4, 2, 256, 256, 40), (2, 2, 64, 64, 160), (2, 3, 300, 300, 64), (4, 2, 100, 77, 80), (1, 1, 17, 5, 8), (2, 2, 128, 130, 48),
+]
+SHAPES_TC = [
+    (2, 8, 1024, 1024, 80), (2, 8, 4096, 4096, 40), (2, 5, 576, 576, 64), (2, 2, 1024, 384, 64), (2, 2, 256, 256, 160),
+    (4, 2, 700, 333, 40), (1, 1, 128, 128, 64), (2, 2, 130, 77, 48),
+]
+
+
+def _check_attn(cuda, shape, impl, dtype=torch.bfloat16, src=None, seed=0):
+    B, H, N, M, d = shape
+    q, k, v = _qkv(B, N, M, H, d, seed, dtype)
+    scale = d ** -0.5
+    kw = src or {}
+    want = orc.indexed_attention(q, k, v, H, scale, **kw)
+    got = ops.attention(q.to(cuda), k.to(cuda), v.to(cuda), H, scale, impl=impl, **kw)
+    torch.cuda.synchronize()
+    err = (got.float().cpu() - want).abs().max().item()
+    assert err < TOL, f"max abs err {err}"
+    return err
+
+
+@pytest.mark.parametrize("shape", SHAPES_MMA)
+def test_attn_mma(cuda, shape):
+    _check_attn(cuda, shape, ops.IEF_IMPL_MMA)
+    assert _cabi.last_attn_impl() == "mma"
+
+
+@pytest.mark.parametrize("shape", SHAPES_TC)
+def test_attn_tcgen05(cuda, shape):
+    _check_attn(cuda, shape, ops.IEF_IMPL_TCGEN05)
+    assert _cabi.last_attn_impl() == "tcgen05"
+
+
+@pytest.mark.parametrize("impl", [ops.IEF_IMPL_MMA, ops.IEF_IMPL_TCGEN05])
+def test_attn_fp16(cuda, impl):
+    _check_attn(cuda, (2, 4, 512, 512, 64), impl, dtype=torch.float16)
+
+
+@pytest.mark.parametrize("impl", [ops.IEF_IMPL_MMA, ops.IEF_IMPL_TCGEN05])
+@pytest.mark.parametrize("name,src", [
+    ("p2p_self_replace", dict(q_src=[0, 1, 2, 2], k_src=[0, 1, 2, 2])),
+    ("masactrl", dict(k_src=[0, 0, 2, 2], v_src=[0, 0, 2, 2])),
+    ("pnp", dict(q_src=[0, 2, 2, 2], k_src=[0, 2, 2, 2])),
+    ("union", dict(k_src=[0, 0, 2, 2], v_src=[0, 0, 2, 2], k_src2=[0, 1, 2, 3], v_src2=[0, 1, 2, 3])),
+])
+def test_attn_row_sources(cuda, impl, name, src):
+    _check_attn(cuda, (4, 2, 640, 640, 40), impl, src=src, seed=3)
+
+
+def test_attn_masactrl_matches_reference_formulation(cuda):
+    """The stacked-queries form of masactrl/model/attention_control.py:37-68 equals per-row source indices."""
+    B, H, N, d = 4, 8, 1024, 80
+    q, k, v = _qkv(B, N, N, H, d, 7)
+    want = orc.masactrl_mutual(q, k, v, H, d ** -0.5)
+    got = ops.attention(q.to(cuda), k.to(cuda), v.to(cuda), H, d ** -0.5, k_src=[0, 0, 2, 2], v_src=[0, 0, 2, 2])
+    assert (got.float().cpu() - want).abs().max().item() < TOL
+
+
+def test_attn_large_logits_lazy_rescale(cuda):
+    """Peaked scores exercise the lazy O-rescale branch of the tcgen05 kernel (threshold 2^8)."""
+    _check_attn(cuda, (1, 2, 512, 2048, 64), ops.IEF_IMPL_TCGEN05, seed=11, src=None)
+    B, H, N, d = 1, 2, 512, 64
+    q, k, v = _qkv(B, N, 2048, H, d, 5, spread=4.0)
+    want = orc.indexed_attention(q, k, v, H, d ** -0.5)
+    got = ops.attention(q.to(cuda), k.to(cuda), v.to(cuda), H, d ** -0.5, impl=ops.IEF_IMPL_TCGEN05)
+    assert (got.float().cpu() - want).abs().max().item() < TOL
+
+
+def test_attn_auto_dispatch(cuda):
+    q, k, v = _qkv(2, 4096, 4096, 8, 40, 0)
+    ops.attention(q.to(cuda), k.to(cuda), v.to(cuda), 8, 40 ** -0.5)
+    assert _cabi.last_attn_impl() == "tcgen05"
+    q, k, v = _qkv(2, 64, 64, 8, 160, 0)
+    ops.attention(q.to(cuda), k.to(cuda), v.to(cuda), 8, 160 ** -0.5)
+    assert _cabi.last_attn_impl() == "mma"
+
+
+def test_attn_head_major_strided_view(cuda):
+    """The reference's '(b h) n d' layout is consumed through strides, without a copy."""
+    B, H, N, d = 2, 4, 512, 64
+    q, k, v = _qkv(B, N, N, H, d, 1)
+    want = orc.plain_attention(q, k, v, H, d ** -0.5)
+    hm = [orc.head_to_batch(t, H).to(cuda).contiguous().view(B, H, N, d).permute(0, 2, 1, 3) for t in (q, k, v)]
+    for impl in (ops.IEF_IMPL_MMA, ops.IEF_IMPL_TCGEN05):
+        got = ops.attention(hm[0], hm[1], hm[2], H, d ** -0.5, impl=impl)
+        assert (got.float().cpu() - want).abs().max().item() < TOL
+
+
+@pytest.mark.parametrize("shape", [(4, 2, 256, 256, 40), (2, 2, 1024, 1024, 80), (2, 3, 100, 77, 64)])
+def test_attn_probs_out(cuda, shape):
+    B, H, N, M, d = shape
+    q, k, v = _qkv(B, N, M, H, d, 2)
+    scale = d ** -0.5
+    want_p = orc.attention_probs(q, k, H, scale)
+    want_o = orc.apply_probs(want_p, v, H)
+    lo = B // 2
+    probs = torch.zeros((B - lo) * H, N, M, device=cuda)
+    slots = [b - lo if b >= lo else -1 for b in range(B)]
+    out = ops.attention(q.to(cuda), k.to(cuda), v.to(cuda), H, scale, probs_out=probs, probs_slot=slots)
+    assert (out.float().cpu() - want_o).abs().max().item() < TOL
+    assert (probs.cpu() - want_p[lo * H:]).abs().max().item() < 5e-3
+    ops.attention(q.to(cuda), k.to(cuda), v.to(cuda), H, scale, probs_out=probs, probs_accum=True, probs_slot=slots)
+    assert (probs.cpu() - 2 * want_p[lo * H:]).abs().max().item() < 1e-2
+
+
+def test_attn_rejects_bad_arguments(cuda):
+    q, k, v = _qkv(2, 64, 64, 2, 36, 0)  # head_dim 36 is not a multiple of 8
+    with pytest.raises(_cabi.IefError):
+        ops.attention(q.to(cuda), k.to(cuda), v.to(cuda), 2, 0.1)
+    q, k, v = _qkv(2, 64, 64, 2, 40, 0)
+    with pytest.raises(_cabi.IefError):
+        ops.attention(q.to(cuda), k.to(cuda), v.to(cuda), 2, 0.1, k_src=[0, 5])
+    with pytest.raises(RuntimeError):
+        ops.attention(q, k, v, 2, 0.1)  # CPU tensors: no fallback
+
+
+# ---------------------------------------------------------------------------------------------------- cross attention edit
+def _edit_tables(n_tgt, M, seed, mode):
+    g = torch.Generator().manual_seed(seed)
+    alpha = (torch.rand(n_tgt, M, generator=g) > 0.3).float()
+    if mode == "replace":
+        mapper = torch.eye(M).repeat(n_tgt, 1, 1)
+        mapper[:, 3, 3] = 0
+        mapper[:, 3, 4] = 0.5
+        mapper[:, 3, 5] = 0.5
+        mapper[:, 10:14] = torch.rand(n_tgt, 4, M, generator=g).softmax(-1)
+        return dict(mapper=mapper), alpha
+    if mode == "refine":
+        idx = torch.arange(M).repeat(n_tgt, 1)
+        idx[:, 5:20] = torch.arange(4, 19)
+        idx[:, 7] = -1
+        idx[:, 30] = -1
+        ra = torch.ones(n_tgt, M)
+        ra[:, 7] = 0
+        ra[:, 30] = 0
+        return dict(mapper=idx, refine_alphas=ra.reshape(n_tgt, 1, 1, M)), alpha
+    return {}, alpha
+
+
+@pytest.mark.parametrize("mode", ["replace", "refine", "none"])
+@pytest.mark.parametrize("equalize", [False, True])
+@pytest.mark.parametrize("shape", [(4, 8, 1024, 77, 80), (6, 2, 300, 77, 40), (4, 8, 4096, 77, 40)])
+def test_cross_attention_edit(cuda, mode, equalize, shape):
+    B, H, N, M, d = shape
+    n_prompts = B // 2
+    n_tgt = n_prompts - 1
+    q, k, v = _qkv(B, N, M, H, d, 4)
+    scale = d ** -0.5
+    tables, alpha = _edit_tables(n_tgt, M, 9, mode)
+    eq = None
+    if equalize:
+        eq = torch.ones(n_tgt, M)
+        eq[:, 2] = 4.0
+        eq[:, 6] = -1.5
+    alpha_table = alpha.reshape(1, n_tgt, 1, 1, M)
+    probs = orc.attention_probs(q, k, H, scale)
+    edited = orc.p2p_edit_probs(probs, H, n_prompts, True, 0, mode=mode, alpha_table=alpha_table, equalizer=eq, **tables)
+    want_o = orc.apply_probs(edited, v, H)
+    dev = {}
+    if mode == "replace":
+        dev["mapper"] = tables["mapper"].to(cuda).contiguous()
+    if mode == "refine":
+        dev["mapper_idx"] = tables["mapper"].to(torch.int32).to(cuda).contiguous()
+        dev["refine_alpha"] = tables["refine_alphas"].reshape(n_tgt, M).to(cuda).contiguous()
+    if eq is not None:
+        dev["equalizer"] = eq.to(cuda).contiguous()
+    edit = ops.CrossEdit({"replace": ops.IEF_EDIT_REPLACE, "refine": ops.IEF_EDIT_REFINE, "none": ops.IEF_EDIT_NONE}[mode], n_tgt, **dev)
+    lo = B // 2
+    base = [-1] * B
+    slot = [0] * B
+    for i in range(1, n_prompts):
+        base[lo + i], slot[lo + i] = lo, i - 1
+    store = torch.zeros(n_prompts * H, N, M, device=cuda)
+    sslot = [b - lo if b >= lo else -1 for b in range(B)]
+    got = ops.cross_attention_edit(q.to(cuda), k.to(cuda), v.to(cuda), H, scale, edit=edit, step_alpha=alpha.to(cuda).contiguous(),
+                                   base_row=base, edit_slot=slot, probs_out=store, store_slot=sslot)
+    torch.cuda.synchronize()
+    assert (got.float().cpu() - want_o).abs().max().item() < TOL * (4 if equalize else 1)
+    assert (store.cpu() - edited[lo * H:]).abs().max().item() < 5e-3 * (4 if equalize else 1)
+
+
+def test_cross_attention_plain_matches_self_kernel(cuda):
+    q, k, v = _qkv(2, 1024, 77, 8, 80, 12)
+    want = orc.plain_attention(q, k, v, 8, 80 ** -0.5)
+    got = ops.cross_attention_edit(q.to(cuda), k.to(cuda), v.to(cuda), 8, 80 ** -0.5)
+    assert (got.float().cpu() - want).abs().max().item() < TOL
+
+
+# ---------------------------------------------------------------------------------------------------- elementwise
+@pytest.mark.parametrize("n", [4 * 4 * 64 * 64, 1000003, 7])
+def test_cfg_ddim_step_bit_exact_fp32(cuda, n):
+    g = torch.Generator().manual_seed(n)
+    eu, ec, x = (torch.randn(n, generator=g) for _ in range(3))
+    a_t, a_p = torch.tensor(0.4217), torch.tensor(0.5531)
+    want = orc.ddim_step(orc.cfg_combine(eu, ec, 7.5), x, a_t, a_p)
+    got = ops.cfg_ddim_step(eu.to(cuda), ec.to(cuda), x.to(cuda), 7.5, float(a_t), float(a_p)).cpu()
+    assert torch.equal(got, want), f"max abs diff {(got - want).abs().max().item()}"
+    want2 = orc.ddim_step(eu, x, a_p, a_t)
+    got2 = ops.cfg_ddim_step(eu.to(cuda), None, x.to(cuda), 0.0, float(a_p), float(a_t)).cpu()
+    assert torch.equal(got2, want2)
+
+
+def test_cfg_ddim_step_bf16(cuda):
+    g = torch.Generator().manual_seed(0)
+    eu, ec, x = (torch.randn(4096, generator=g).to(torch.bfloat16) for _ in range(3))
+    want = orc.ddim_step(orc.cfg_combine(eu.float(), ec.float(), 7.5), x.float(), torch.tensor(0.3), torch.tensor(0.35))
+    got = ops.cfg_ddim_step(eu.to(cuda), ec.to(cuda), x.to(cuda), 7.5, 0.3, 0.35).float().cpu()
+    assert (got - want).abs().max().item() < 0.1 and torch.allclose(got, want, rtol=1e-2, atol=2e-2)
+
+
+def test_store_accumulate_bit_exact(cuda):
+    g = torch.Generator().manual_seed(1)
+    sizes = [16 * 256 * 77, 16 * 1024 * 77, 5, 16 * 64 * 64, 3 * 1024 * 1024 + 1]
+    dst = [torch.randn(s, generator=g) for s in sizes]
+    src = [torch.randn(s, generator=g) for s in sizes]
+    want = [d + s for d, s in zip(dst, src)]
+    d_dev = [d.to(cuda) for d in dst]
+    ops.store_accumulate(d_dev, [s.to(cuda) for s in src])
+    for a, b in zip(d_dev, want):
+        assert torch.equal(a.cpu(), b)
+
+
+def test_local_blend(cuda):
+    g = torch.Generator().manual_seed(2)
+    heads = [8, 8, 8, 8, 8]
+    maps = [torch.rand(2 * h, 256, 77, generator=g) ** 4 for h in heads]
+    alpha = torch.zeros(2, 1, 1, 1, 1, 77)
+    alpha[0, ..., 3] = 1
+    alpha[1, ..., 3] = 1
+    alpha[1, ..., 4] = 1
+    x = torch.randn(2, 4, 64, 64, generator=g)
+    want, want_mask = orc.local_blend(x, maps, alpha, 0.3, return_mask=True)
+    got, mask = ops.local_blend(x.clone().to(cuda), [m.to(cuda) for m in maps], 2, alpha.reshape(2, 77).to(cuda), 0.3, return_mask=True)
+    mism = (mask.cpu() != want_mask).float().mean().item()
+    assert mism < 1e-3, f"mask mismatch fraction {mism}"
+    if mism == 0:
+        assert torch.equal(got.cpu(), want)

@@ -1,0 +1,12 @@
+#!/usr/bin/env bash
+# Runs the GPU test groups in separate processes (a faulting kernel poisons only its own process).
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
+nproc >> gpurun_out/gpu.txt
+run() { name=$1; shift; echo "=== $name" ; timeout 600 python -m pytest tests/test_gpu_kernels.py -q -m gpu -p no:cacheprovider --timeout=300 -k "$1" > gpurun_out/t_$name.log 2>&1; echo "exit $?"; tail -5 gpurun_out/t_$name.log; }
+run probe "umma_probe"
+run mma "attn_mma or probs_out or rejects"
+run tc "tcgen05 or fp16 or row_sources or masactrl or lazy or auto or strided"
+run cross "cross_attention"
+run elem "ddim or accumulate or local_blend"
+echo "=== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "exit $?"; tail -3 gpurun_out/smoke.log
