@@ -9,6 +9,7 @@ Everything a test needs to rebuild the inputs (config, seeds, prompts) is stored
 Compositions the reference cannot execute as shipped (AttentionStore + edit, LocalBlend — SURVEY.md facts 0.5-0.7)
 are generated from the reference classes re-composed the upstream Prompt-to-Prompt way and are labelled "recomposed".
 """
+import dataclasses
 import os
 import sys
 
@@ -23,6 +24,7 @@ from image_editing_framework_b200.standin import make_pipeline, tiny_config, Wor
 from image_editing_framework_b200.standin.unet import UNetConfig  # noqa: E402
 
 CPU = torch.device("cpu")
+LAT = 8  # golden latents are 8x8 (tokens 64/16/4/1) to keep the committed fixtures small
 
 PROMPT_CASES = [
     # (source, target, kind)
@@ -116,15 +118,17 @@ def gen_p2p():
         ref.register.register_attention_control(pipe, ctrl)
         rec = Recorder(pipe.unet, keep)
         context = _context(pipe, prompts)
-        latent = _latent(1, (1, 4, 16, 16))
-        latents = latent.expand(2, 4, 16, 16)
+        latent = _latent(1, (1, 4, LAT, LAT))
+        latents = latent.expand(2, 4, LAT, LAT)
         per_step = []
         with torch.no_grad():
             for i, t in enumerate(pipe.scheduler.timesteps):
                 rec.step = i
                 latents = editor.diffusion_step(pipe, ctrl, latents, context, t, 7.5, False)
                 per_step.append(latents.clone())
-        g = dict(prompts=prompts, steps=steps, keep=keep, latent_seed=1, pipe_seed=0, guidance=7.5, layer_outputs=rec.records,
+        if kind in ("store", "empty"):
+            rec.records = {}
+        g = dict(prompts=prompts, steps=steps, keep=keep, latent_seed=1, pipe_seed=0, guidance=7.5, layer_outputs=rec.records, latent_hw=LAT,
                  latents_per_step=per_step, num_att_layers=ctrl.num_att_layers, cur_step=ctrl.cur_step)
         if kind == "store":
             avg = ctrl.get_average_attention()
@@ -157,6 +161,7 @@ def gen_p2p_localblend():
             return super().forward(attn, is_cross, place_in_unet)
 
         between_steps = AB.AttentionStore.between_steps
+        get_empty_store = staticmethod(AB.AttentionStore.get_empty_store)
 
     cfg = UNetConfig(sample_size=64, block_out_channels=(16, 32, 32, 32), num_heads=(2, 2, 2, 2), cross_attention_dim=32, norm_num_groups=8, name="tiny64")
     pipe = make_pipeline(cfg, seed=3)
@@ -175,7 +180,7 @@ def gen_p2p_localblend():
             per_step.append(latents.clone())
     maps = ctrl.attention_store["down_cross"][2:4] + ctrl.attention_store["up_cross"][:3]
     _save("p2p_localblend.pt", dict(recomposed=True, prompts=prompts, steps=steps, latent_seed=5, pipe_seed=3, guidance=7.5,
-                                    config=cfg, blend_words=[["cat"], ["dog"]], latents_per_step=per_step,
+                                    config=dataclasses.asdict(cfg), blend_words=[["cat"], ["dog"]], latents_per_step=per_step,
                                     store_16=[m.clone() for m in maps]))
     # stand-alone LocalBlend known-answer on synthetic maps
     g = torch.Generator().manual_seed(8)
@@ -195,7 +200,7 @@ def gen_masactrl():
     ref.register.regiter_attention_editor_diffusers(pipe, ctrl)
     rec = Recorder(pipe.unet, keep)
     context = _context(pipe, prompts)
-    init = _latent(2, (1, 4, 16, 16))
+    init = _latent(2, (1, 4, LAT, LAT))
     latents = torch.cat([init, init])
     per_step = []
     with torch.no_grad():
@@ -206,7 +211,7 @@ def gen_masactrl():
             latents = pipe.scheduler.step(nu + 7.5 * (nc - nu), t, latents, return_dict=True)["prev_sample"]  # sd_utils.py:107-113
             per_step.append(latents.clone())
     _save("masactrl.pt", dict(prompts=prompts, steps=steps, keep=keep, latent_seed=2, pipe_seed=1, guidance=7.5, start_step=1, start_layer=10,
-                              layer_outputs=rec.records, latents_per_step=per_step, num_att_layers=ctrl.num_att_layers))
+                              layer_outputs=rec.records, latents_per_step=per_step, num_att_layers=ctrl.num_att_layers, latent_hw=LAT))
 
 
 def gen_pnp():
@@ -221,7 +226,7 @@ def gen_pnp():
     ref.register.register_conv_control_efficient(pipe, ts[:f_t])
     rec = Recorder(pipe.unet, keep)
     context = _context(pipe, prompts)
-    init = _latent(3, (1, 4, 16, 16))
+    init = _latent(3, (1, 4, LAT, LAT))
     latents = torch.cat([init, init])
     per_step = []
     with torch.no_grad():
@@ -233,7 +238,7 @@ def gen_pnp():
             latents = pipe.scheduler.step(nu + 7.5 * (nc - nu), t, latents).prev_sample      # pnp/model/sd_utils.py:99-107
             per_step.append(latents.clone())
     _save("pnp.pt", dict(prompts=prompts, steps=steps, keep=keep, latent_seed=3, pipe_seed=2, guidance=7.5, pnp_attn_t=0.5, pnp_f_t=0.8,
-                         layer_outputs=rec.records, latents_per_step=per_step))
+                         layer_outputs=rec.records, latents_per_step=per_step, latent_hw=LAT))
 
 
 def gen_pix2pix_zero():
@@ -243,11 +248,77 @@ def gen_pix2pix_zero():
     rec = Recorder(unet, (0,))
     prompts = ["a photo of a cat"]
     context = _context(pipe, prompts)
-    x = _latent(4, (1, 4, 16, 16))
+    x = _latent(4, (1, 4, LAT, LAT))
     with torch.no_grad():
         out = unet(torch.cat([x] * 2), torch.tensor(981), encoder_hidden_states=context).sample
     probs = {name: m.attn_probs.clone() for name, m in unet.named_modules() if type(m).__name__ == "Attention" and "attn2" in name}
-    _save("pix2pix_zero.pt", dict(prompts=prompts, latent_seed=4, pipe_seed=4, t=981, unet_out=out, layer_outputs=rec.records[0], cross_probs=probs))
+    _save("pix2pix_zero.pt", dict(prompts=prompts, latent_seed=4, pipe_seed=4, t=981, unet_out=out, layer_outputs=rec.records[0], cross_probs=probs, latent_hw=LAT))
+
+
+def gen_oracle_pins():
+    """Small known-answer vectors straight from the reference's controller METHODS on random tensors: they pin every
+    function of oracle/controlled_attention.py without needing /root/reference at test time."""
+    p2p, masa, pnp = load_reference("p2p"), load_reference("masactrl"), load_reference("pnp")
+    from image_editing_framework_b200.standin import Attention
+    tok = WordPieceTokenizer()
+    g = torch.Generator().manual_seed(10)
+    H, N, M, d, steps = 2, 32, 77, 8, 10
+    out = dict(H=H, N=N, M=M, d=d, steps=steps, seed=10)
+    prompts = ["a squirrel eating a burger", "a lion eating a burger", "a hippopotamus eating a burger"]
+    rprompts = ["a bowl of soup", "a bowl of pea soup", "a large bowl of hot soup"]
+    cross = torch.randn(6 * H, N, M, generator=g).softmax(-1)
+    selfp = torch.randn(6 * H, N, N, generator=g).softmax(-1)
+    big = torch.randn(6 * H, 257, 257, generator=torch.Generator().manual_seed(12)).softmax(-1)  # > 16^2 tokens: never replaced
+    out.update(cross=cross, selfp=selfp, big_seed=12, prompts=prompts, rprompts=rprompts)
+
+    def run(ctrl, probs, is_cross, step):
+        ctrl.num_att_layers, ctrl.cur_step, ctrl.cur_att_layer = 100, step, 0
+        return ctrl(probs.clone(), is_cross, "down")
+
+    kw = dict(tokenizer=tok, num_steps=steps, cross_replace_steps={"default_": 0.8, "burger": (0.0, 0.3)}, self_replace_steps=0.4, device=CPU)
+    rep = p2p.attention_control.AttentionReplace(prompts=prompts, **kw)
+    kw["cross_replace_steps"] = 0.8
+    ref_ = p2p.attention_control.AttentionRefine(prompts=rprompts, **kw)
+    eq = p2p.seq_aligner.get_equalizer(tok, prompts[1], ("lion",), (2.0, -1.0))
+    rew = p2p.attention_control.AttentionReweight(prompts=prompts, equalizer=eq, controller=rep, **kw)
+    rew0 = p2p.attention_control.AttentionReweight(prompts=prompts, equalizer=eq, controller=None, **kw)
+    for name, c in (("replace", rep), ("refine", ref_), ("reweight_chain", rew), ("reweight", rew0)):
+        out[name] = {f"cross_step{s}": run(c, cross, True, s) for s in (0, 2, 9)}
+        out[name].update({f"self_step{s}": run(c, selfp, False, s) for s in (0, 5)})
+        out[name]["self_big_unchanged"] = bool(torch.equal(run(c, big, False, 0), big))
+    out["tables"] = dict(replace_mapper=rep.mapper, replace_alpha=rep.cross_replace_alpha, refine_mapper=ref_.mapper, refine_alphas=ref_.alphas,
+                         refine_alpha=ref_.cross_replace_alpha, equalizer=eq, num_self_replace=rep.num_self_replace)
+    # MasaCtrl mutual self-attention on '(b h) n d' tensors
+    q, k, v = (torch.randn(4 * H, N, d, generator=g) for _ in range(3))
+    ed = masa.attention_control.MutualSelfAttentionControl(0, 0, total_steps=4)
+    ed.num_att_layers = 100
+    sim = torch.einsum("bid,bjd->bij", q, k) * d ** -0.5
+    out["masactrl"] = dict(q=q, k=k, v=v, out=ed.forward(q, k, v, sim, sim.softmax(-1), False, "up", H, scale=d ** -0.5))
+    out["masactrl_plain"] = masa.attention_base.AttentionBase.forward(ed, q, k, v, sim, sim.softmax(-1), False, "up", H, scale=d ** -0.5)
+    # PnP closure on a stand-in Attention
+    torch.manual_seed(11)
+    attn = Attention(16, None, H, d).eval()
+
+    class Holder:
+        pass
+    hold = Holder()
+    hold.unet = Holder()
+    blk = Holder()
+    blk.attn1 = attn
+    att = Holder()
+    att.transformer_blocks = [blk]
+    up = Holder()
+    up.attentions = [att, att, att]
+    hold.unet.up_blocks = [None, up, up, up]
+    pnp.register.register_attention_control_efficient(hold, torch.tensor([981, 961]))
+    x = torch.randn(4, N, 16, generator=g)
+    attn.t = 981
+    with torch.no_grad():
+        inj = attn.forward(x)
+        attn.t = 1
+        plain = attn.forward(x)
+    out["pnp"] = dict(x=x, state=attn.state_dict(), injected=inj, plain=plain)
+    _save("oracle_pins.pt", out)
 
 
 def gen_ddim():
@@ -268,6 +339,6 @@ def gen_ddim():
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["aligner", "ddim", "p2p", "masactrl", "pnp", "pix2pix_zero", "p2p_localblend"]
+    which = sys.argv[1:] or ["aligner", "oracle_pins", "ddim", "p2p", "masactrl", "pnp", "pix2pix_zero", "p2p_localblend"]
     for w in which:
         globals()["gen_" + w]()

@@ -1,0 +1,155 @@
+"""The golden scenarios (tests/golden/make_goldens.py) replayed through THIS repo's register / controller / driver code.
+Shared by the CPU host-logic tests (oracle-backed fake ops) and the GPU parity tests (real kernels)."""
+import os
+
+import torch
+
+from image_editing_framework_b200 import p2p, masactrl, pnp, pix2pix_zero, editing
+from image_editing_framework_b200.ddim import FusedDDIM
+from image_editing_framework_b200.standin import make_pipeline, tiny_config
+from image_editing_framework_b200.standin.unet import UNetConfig
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden(name):
+    return torch.load(os.path.join(GOLDEN_DIR, name), map_location="cpu", weights_only=False)
+
+
+class Recorder:
+    def __init__(self, unet, keep):
+        self.keep, self.step, self.records = set(keep), 0, {}
+        for m in unet.modules():
+            if type(m).__name__ == "Attention":
+                m.forward = self._wrap(m.forward)
+
+    def _wrap(self, inner):
+        def fwd(*a, **kw):
+            out = inner(*a, **kw)
+            if self.step in self.keep:
+                self.records.setdefault(self.step, []).append(out.detach().float().cpu())
+            return out
+        return fwd
+
+
+def latent(seed, shape, device):
+    return torch.randn(shape, generator=torch.Generator().manual_seed(seed)).to(device)
+
+
+def psnr(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    mse = ((a - b) ** 2).mean().item()
+    peak = (b.max() - b.min()).item()
+    return float("inf") if mse == 0 else 10 * torch.log10(torch.tensor(peak * peak / mse)).item()
+
+
+def run_p2p(kind, g, device):
+    pipe = make_pipeline(tiny_config(), seed=g["pipe_seed"], device=device)
+    prompts, steps = g["prompts"], g["steps"]
+    common = dict(prompts=prompts, tokenizer=pipe.tokenizer, num_steps=steps, cross_replace_steps=0.8, self_replace_steps=0.6, device=device)
+    if kind == "replace":
+        ctrl = p2p.AttentionReplace(**common)
+    elif kind == "refine":
+        ctrl = p2p.AttentionRefine(**common)
+    elif kind == "reweight":
+        eq = p2p.seq_aligner.get_equalizer(pipe.tokenizer, prompts[1], ("dog",), (3.0,))
+        ctrl = p2p.AttentionReweight(equalizer=eq, controller=p2p.AttentionReplace(**common), **common)
+    elif kind == "store":
+        ctrl = p2p.AttentionStore(False)
+    else:
+        ctrl = p2p.EmptyControl(False)
+    pipe.scheduler.set_timesteps(steps)
+    p2p.register_attention_control(pipe, ctrl)
+    rec = Recorder(pipe.unet, g["keep"])
+    context = editing.encode_prompts(pipe, prompts)
+    hw = g["latent_hw"]
+    latents = latent(g["latent_seed"], (1, 4, hw, hw), device).expand(2, 4, hw, hw).contiguous()
+    fused = FusedDDIM(pipe.scheduler)
+    per_step = []
+    with torch.no_grad():
+        for i, t in enumerate(pipe.scheduler.timesteps.tolist()):
+            rec.step = i
+            noise = pipe.unet(torch.cat([latents] * 2), t, encoder_hidden_states=context)["sample"]
+            latents = ctrl.step_callback(fused.step(noise, t, latents, g["guidance"]))
+            per_step.append(latents.float().cpu())
+    return ctrl, rec.records, per_step
+
+
+def run_masactrl(g, device):
+    pipe = make_pipeline(tiny_config(), seed=g["pipe_seed"], device=device)
+    steps = g["steps"]
+    pipe.scheduler.set_timesteps(steps)
+    ctrl = masactrl.MutualSelfAttentionControl(g["start_step"], g["start_layer"], total_steps=steps)
+    masactrl.regiter_attention_editor_diffusers(pipe, ctrl)
+    rec = Recorder(pipe.unet, g["keep"])
+    context = editing.encode_prompts(pipe, g["prompts"])
+    hw = g["latent_hw"]
+    init = latent(g["latent_seed"], (1, 4, hw, hw), device)
+    latents = torch.cat([init, init])
+    fused = FusedDDIM(pipe.scheduler)
+    per_step = []
+    with torch.no_grad():
+        for i, t in enumerate(pipe.scheduler.timesteps.tolist()):
+            rec.step = i
+            noise = pipe.unet(torch.cat([latents] * 2), t, encoder_hidden_states=context).sample
+            latents = fused.step(noise, t, latents, g["guidance"])
+            per_step.append(latents.float().cpu())
+    return ctrl, rec.records, per_step
+
+
+def run_pnp(g, device):
+    pipe = make_pipeline(tiny_config(), seed=g["pipe_seed"], device=device)
+    steps = g["steps"]
+    pipe.scheduler.set_timesteps(steps)
+    ts = pipe.scheduler.timesteps
+    pnp.register_attention_control_efficient(pipe, ts[:int(steps * g["pnp_attn_t"])])
+    pnp.register_conv_control_efficient(pipe, ts[:int(steps * g["pnp_f_t"])])
+    rec = Recorder(pipe.unet, g["keep"])
+    context = editing.encode_prompts(pipe, g["prompts"])
+    hw = g["latent_hw"]
+    init = latent(g["latent_seed"], (1, 4, hw, hw), device)
+    latents = torch.cat([init, init])
+    fused = FusedDDIM(pipe.scheduler)
+    per_step = []
+    with torch.no_grad():
+        for i, t in enumerate(ts.tolist()):
+            rec.step = i
+            pnp.register_time(pipe, t)
+            noise = pipe.unet(torch.cat([latents] * 2), t, encoder_hidden_states=context).sample
+            latents = fused.step(noise, t, latents, g["guidance"])
+            per_step.append(latents.float().cpu())
+    return rec.records, per_step
+
+
+def run_pix2pix_zero(g, device):
+    pipe = make_pipeline(tiny_config(), seed=g["pipe_seed"], device=device)
+    unet, originals = pix2pix_zero.prep_unet(pipe.unet)
+    rec = Recorder(unet, (0,))
+    context = editing.encode_prompts(pipe, g["prompts"])
+    hw = g["latent_hw"]
+    x = latent(g["latent_seed"], (1, 4, hw, hw), device)
+    with torch.no_grad():
+        out = unet(torch.cat([x] * 2), g["t"], encoder_hidden_states=context).sample
+    probs = {n: m.attn_probs.float().cpu() for n, m in unet.named_modules() if type(m).__name__ == "Attention" and "attn2" in n}
+    return out.float().cpu(), rec.records[0], probs, (unet, originals)
+
+
+def run_p2p_localblend(g, device):
+    cfg = UNetConfig(**g["config"])
+    pipe = make_pipeline(cfg, seed=g["pipe_seed"], device=device)
+    prompts, steps = g["prompts"], g["steps"]
+    lb = p2p.LocalBlend(pipe.tokenizer, prompts, g["blend_words"], device=device)
+    ctrl = p2p.AttentionReplace(prompts, pipe.tokenizer, steps, 0.8, 0.6, lb, device=device)
+    pipe.scheduler.set_timesteps(steps)
+    p2p.register_attention_control(pipe, ctrl)
+    context = editing.encode_prompts(pipe, prompts)
+    latents = latent(g["latent_seed"], (1, 4, 64, 64), device).expand(2, 4, 64, 64).contiguous()
+    fused = FusedDDIM(pipe.scheduler)
+    per_step = []
+    with torch.no_grad():
+        for t in pipe.scheduler.timesteps.tolist():
+            noise = pipe.unet(torch.cat([latents] * 2), t, encoder_hidden_states=context)["sample"]
+            latents = ctrl.step_callback(fused.step(noise, t, latents, g["guidance"]))
+            per_step.append(latents.float().cpu())
+    maps = ctrl.attention_store["down_cross"][2:4] + ctrl.attention_store["up_cross"][:3]
+    return ctrl, per_step, [m.float().cpu() for m in maps]

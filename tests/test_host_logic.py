@@ -1,0 +1,316 @@
+"""CPU suite: goldens produced by the reference's own code pin (a) the bit-exact host-side integer logic, (b) the oracle,
+(c) the controller / register / driver host logic (driven here through oracle-backed fake ops, see tests/cpu_backend.py)."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from image_editing_framework_b200 import p2p, _cabi
+from image_editing_framework_b200.p2p import seq_aligner, ptp_utils
+from image_editing_framework_b200.standin import WordPieceTokenizer, make_pipeline, tiny_config, sd15_config, sd21_config, sdxl_config, attention_geometry
+from oracle import controlled_attention as orc
+from oracle import reference_loader
+
+import cpu_backend
+import scenarios
+from scenarios import golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ------------------------------------------------------------------------------------------------ C ABI
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "ief_b200.h")).read()
+    declared = set(re.findall(r"\b(ief_[a-z0-9_]+)\s*\(", header))
+    declared -= {"ief_tensor4", "ief_attn_params"}
+    assert declared == set(_cabi.EXPORTS), declared ^ set(_cabi.EXPORTS)
+    lib = _cabi.lib()
+    for sym in declared:
+        assert getattr(lib, sym) is not None
+    assert lib.ief_abi_version() == _cabi.IEF_ABI_VERSION
+
+
+def test_struct_sizes_match_header_layout():
+    import ctypes as C
+    # 4 tensor4 (32 B each) + 6 int32 + float + int32 (=160) + 5 pointers + ptr + int32(+pad) + 2 pointers
+    assert C.sizeof(_cabi.Tensor4) == 32
+    assert C.sizeof(_cabi.AttnParams) == 128 + 32 + 5 * 8 + 8 + 8 + 8 + 8
+    assert C.sizeof(_cabi.CrossParams) == 128 + 32 + 8 + 8 + 8 + 5 * 8 + 8 + 8 + 8
+
+
+def test_ops_refuse_cpu_tensors():
+    from image_editing_framework_b200 import ops
+    q = torch.zeros(1, 8, 16, dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.attention(q, q, q, 2, 1.0)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.cfg_ddim_step(torch.zeros(4), None, torch.zeros(4), 0.0, 0.5, 0.6)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "image_editing_framework_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{f} imports the oracle"
+                assert "/root/reference" not in src
+
+
+# ------------------------------------------------------------------------------------------------ token aligner (bit-exact)
+@pytest.fixture(scope="module")
+def aligner_golden():
+    return golden("aligner.pt")
+
+
+def test_tokenizer_is_the_one_the_goldens_used(aligner_golden):
+    tok = WordPieceTokenizer()
+    for c in aligner_golden["cases"]:
+        assert tok.encode(c["source"]) == c["src_ids"] and tok.encode(c["target"]) == c["tgt_ids"]
+    ids = tok.encode("a hippopotamus")
+    assert len(ids) == 2 + 1 + 3 and "".join(tok.decode([i]) for i in ids[2:-1]) == "hippopotamus"
+
+
+def test_mappers_bit_exact(aligner_golden):
+    tok = WordPieceTokenizer()
+    for c in aligner_golden["cases"]:
+        pr = [c["source"], c["target"]]
+        m, a = seq_aligner.get_refinement_mapper(pr, tok)
+        assert m.dtype == torch.int64 and torch.equal(m, c["refinement_mapper"]), c["target"]
+        assert torch.equal(a, c["refinement_alphas"])
+        if c["kind"] == "replace":
+            r = seq_aligner.get_replacement_mapper(pr, tok)
+            assert r.dtype == torch.float32 and torch.equal(r, c["replacement_mapper"]), c["target"]
+        for w, inds in c["word_inds"].items():
+            assert seq_aligner.get_word_inds(c["target"], w, tok).tolist() == inds
+        for i, inds in enumerate(c["word_inds_by_pos"]):
+            assert seq_aligner.get_word_inds(c["target"], i, tok).tolist() == inds
+        words = c["target"].split(" ")
+        assert torch.equal(seq_aligner.get_equalizer(tok, c["target"], (words[-1],), (2.0,)), c["equalizer"])
+        assert torch.equal(ptp_utils.get_time_words_attention_alpha(pr, 10, 0.8, tok), c["alpha_float"])
+        assert torch.equal(ptp_utils.get_time_words_attention_alpha(pr, 10, {"default_": 1.0, words[-1]: (0.2, 0.6)}, tok), c["alpha_dict"])
+    mg = aligner_golden["multi"]
+    assert torch.equal(seq_aligner.get_replacement_mapper(mg["prompts"], tok), mg["replacement"])
+    m, a = seq_aligner.get_refinement_mapper(mg["prompts"], tok)
+    assert torch.equal(m, mg["refinement"][0]) and torch.equal(a, mg["refinement"][1])
+    assert torch.equal(ptp_utils.get_time_words_attention_alpha(mg["prompts"], 50, (0.1, 0.7), tok), mg["alpha"])
+
+
+def test_refinement_mapper_has_gaps_and_minus_one(aligner_golden):
+    c = [c for c in aligner_golden["cases"] if c["target"].startswith("a watercolor")][0]
+    assert (c["refinement_mapper"] == -1).any() and (c["refinement_alphas"] == 0).any()
+
+
+def test_replacement_rejects_different_word_counts():
+    with pytest.raises(ValueError):
+        seq_aligner.get_replacement_mapper(["a cat", "a big cat"], WordPieceTokenizer())
+
+
+@pytest.mark.skipif(not reference_loader.reference_available(), reason="reference tree only exists in the build container")
+def test_aligner_matches_live_reference_on_random_prompts():
+    ref = reference_loader.load_reference("p2p")
+    tok = WordPieceTokenizer()
+    rng = np.random.default_rng(0)
+    vocab = ["a", "the", "cat", "dog", "hippopotamus", "on", "under", "table", "watercolor", "painting", "of", "blue", "squirrel", "eats"]
+    for _ in range(40):
+        n = int(rng.integers(1, 9))
+        x = " ".join(rng.choice(vocab, n))
+        y_same = x.split(" ")
+        for j in rng.choice(n, size=min(2, n), replace=False):
+            y_same[j] = str(rng.choice(vocab))
+        y_same = " ".join(y_same)
+        y_any = " ".join(rng.choice(vocab, int(rng.integers(1, 12))))
+        assert torch.equal(seq_aligner.get_replacement_mapper([x, y_same], tok), ref.seq_aligner.get_replacement_mapper([x, y_same], tok))
+        a, b = seq_aligner.get_refinement_mapper([x, y_any], tok), ref.seq_aligner.get_refinement_mapper([x, y_any], tok)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+
+
+# ------------------------------------------------------------------------------------------------ oracle pinned by reference outputs
+@pytest.fixture(scope="module")
+def pins():
+    return golden("oracle_pins.pt")
+
+
+@pytest.mark.parametrize("name,mode", [("replace", "replace"), ("refine", "refine"), ("reweight_chain", "replace"), ("reweight", "none")])
+def test_oracle_p2p_edit_matches_reference(pins, name, mode):
+    t, H = pins["tables"], pins["H"]
+    kw = dict(mode=mode, num_self_replace=t["num_self_replace"])
+    if name in ("replace", "reweight_chain"):
+        kw.update(mapper=t["replace_mapper"], alpha_table=t["replace_alpha"])
+    elif name == "refine":
+        kw.update(mapper=t["refine_mapper"], refine_alphas=t["refine_alphas"], alpha_table=t["refine_alpha"])
+    else:
+        kw.update(alpha_table=t["replace_alpha"])
+    if name.startswith("reweight"):
+        kw["equalizer"] = t["equalizer"]
+    for key, want in pins[name].items():
+        if key == "self_big_unchanged":
+            big = torch.randn(6 * H, 257, 257, generator=torch.Generator().manual_seed(pins["big_seed"])).softmax(-1)
+            assert want and torch.equal(orc.p2p_edit_probs(big, H, 3, False, 0, **kw), big)
+            continue
+        is_cross = key.startswith("cross")
+        step = int(key.split("step")[1])
+        got = orc.p2p_edit_probs(pins["cross"] if is_cross else pins["selfp"], H, 3, is_cross, step, **kw)
+        assert torch.allclose(got, want, atol=1e-6, rtol=1e-5), f"{name}/{key}: {(got - want).abs().max().item()}"
+
+
+def test_oracle_masactrl_and_indexed_form_match_reference(pins):
+    m, H, d = pins["masactrl"], pins["H"], pins["d"]
+    q, k, v = (orc.batch_to_head(t, H) for t in (m["q"], m["k"], m["v"]))   # '(b h) n d' -> [B, N, H*d]
+    got = orc.masactrl_mutual(q, k, v, H, d ** -0.5)
+    assert torch.allclose(got, m["out"], atol=1e-6, rtol=1e-5)
+    idx = orc.indexed_attention(q, k, v, H, d ** -0.5, k_src=[0, 0, 2, 2], v_src=[0, 0, 2, 2])
+    assert torch.allclose(idx, m["out"], atol=1e-6, rtol=1e-5)
+    assert torch.allclose(orc.plain_attention(q, k, v, H, d ** -0.5), pins["masactrl_plain"], atol=1e-6, rtol=1e-5)
+
+
+def test_oracle_pnp_injection_matches_reference(pins):
+    from image_editing_framework_b200.standin import Attention
+    p, H, d = pins["pnp"], pins["H"], pins["d"]
+    attn = Attention(16, None, H, d)
+    attn.load_state_dict(p["state"])
+    x = p["x"]
+    with torch.no_grad():
+        q, k, v = attn.to_q(x), attn.to_k(x), attn.to_v(x)
+        qi, ki = orc.pnp_inject_qk(q, k)
+        inj = attn.to_out[0](orc.plain_attention(qi, ki, v, H, attn.scale))
+        plain = attn.to_out[0](orc.plain_attention(q, k, v, H, attn.scale))
+        idx = attn.to_out[0](orc.indexed_attention(q, k, v, H, attn.scale, q_src=[0, 2, 2, 2], k_src=[0, 2, 2, 2]))
+    assert torch.allclose(inj, p["injected"], atol=1e-6, rtol=1e-5)
+    assert torch.allclose(plain, p["plain"], atol=1e-6, rtol=1e-5)
+    assert torch.allclose(idx, p["injected"], atol=1e-6, rtol=1e-5)
+
+
+def test_oracle_ddim_matches_reference():
+    g = golden("ddim.pt")
+    gen = torch.Generator().manual_seed(g["seed"])
+    eps, x = torch.randn(1, 4, 64, 64, generator=gen), torch.randn(1, 4, 64, 64, generator=gen)
+    ac = g["alphas_cumprod"]
+    for t, want in g["reverse"].items():
+        cur = min(999, t - 20)
+        a_cur = ac[cur] if cur >= 0 else ac[0]
+        assert torch.equal(orc.ddim_step(eps, x, a_cur, ac[t]), want)
+    eu, ec = torch.randn(2, 4, 64, 64, generator=gen), torch.randn(2, 4, 64, 64, generator=gen)
+    xx = torch.randn(2, 4, 64, 64, generator=gen)
+    for t, want in g["forward"].items():
+        prev = t - 20
+        a_prev = ac[prev] if prev >= 0 else ac[0]
+        assert torch.equal(orc.ddim_step(orc.cfg_combine(eu, ec, g["guidance"]), xx, ac[t], a_prev), want)
+    assert g["timesteps"].tolist() == list(range(981, 0, -20))
+
+
+def test_oracle_local_blend_matches_reference():
+    g = golden("local_blend.pt")
+    gen = torch.Generator().manual_seed(g["seed"])
+    syn = [torch.rand(16, 256, 77, generator=gen) ** 4 for _ in range(5)]
+    x = torch.randn(2, 4, 64, 64, generator=gen)
+    got = orc.local_blend(x, syn, g["alpha_layers"], 0.3)
+    assert torch.equal(got, g["x_out"])
+
+
+# ------------------------------------------------------------------------------------------------ stand-in geometry
+def test_standin_attention_geometry_matches_survey():
+    sd = attention_geometry(sd15_config())
+    assert len(sd) == 16 and [(n, d) for _, n, _, d in sd] == [(4096, 40)] * 2 + [(1024, 80)] * 2 + [(256, 160)] * 2 + [(64, 160)] + \
+        [(256, 160)] * 3 + [(1024, 80)] * 3 + [(4096, 40)] * 3
+    sd21 = attention_geometry(sd21_config())
+    assert len(sd21) == 16 and {d for *_, d in sd21} == {64} and sd21[0][1] == 9216
+    xl = attention_geometry(sdxl_config())
+    assert len(xl) == 70 and {d for *_, d in xl} == {64} and sum(1 for _, n, _, _ in xl if n == 4096) == 10
+
+
+def test_tiny_unet_has_32_attention_layers_in_reference_discovery_order():
+    pipe = make_pipeline(tiny_config(), seed=0)
+    ctrl = p2p.EmptyControl(False)
+    p2p.register_attention_control(pipe, ctrl)
+    assert ctrl.num_att_layers == 32
+    p2p.unregister_attention_control(pipe, ctrl)
+    assert ctrl.num_att_layers == 0 and all(not hasattr(m, "_ief") for m in pipe.unet.modules())
+
+
+# ------------------------------------------------------------------------------------------------ host logic end to end (fake ops)
+LAYER_TOL = 2e-4  # fp32 everywhere: only reduction-order noise
+
+
+def _compare(records, per_step, g, tol=LAYER_TOL):
+    for step, outs in g["layer_outputs"].items():
+        got = records[step]
+        assert len(got) == len(outs)
+        for i, (a, b) in enumerate(zip(got, outs)):
+            assert a.shape == b.shape and (a - b).abs().max().item() < tol, f"step {step} layer {i}: {(a - b).abs().max().item()}"
+    for i, (a, b) in enumerate(zip(per_step, g["latents_per_step"])):
+        assert (a - b).abs().max().item() < tol * 5, f"latents after step {i}: {(a - b).abs().max().item()}"
+
+
+@pytest.mark.parametrize("kind", ["replace", "refine", "reweight", "store", "empty"])
+def test_p2p_host_logic_reproduces_reference(monkeypatch, kind):
+    cpu_backend.install(monkeypatch)
+    g = golden("p2p.pt")[kind]
+    ctrl, records, per_step = scenarios.run_p2p(kind, g, torch.device("cpu"))
+    assert ctrl.num_att_layers == g["num_att_layers"] and ctrl.cur_step == g["cur_step"] and ctrl.cur_att_layer == 0
+    _compare(records, per_step, g)
+    if kind == "store":
+        avg = ctrl.get_average_attention()
+        for key, maps in g["average_attention"].items():
+            assert len(avg[key]) == len(maps)
+            for a, b in zip(avg[key], maps):
+                assert a.shape == b.shape and torch.allclose(a, b, atol=1e-5)
+
+
+def test_masactrl_host_logic_reproduces_reference(monkeypatch):
+    cpu_backend.install(monkeypatch)
+    g = golden("masactrl.pt")
+    ctrl, records, per_step = scenarios.run_masactrl(g, torch.device("cpu"))
+    assert ctrl.num_att_layers == g["num_att_layers"] == 32
+    _compare(records, per_step, g)
+
+
+def test_pnp_host_logic_reproduces_reference(monkeypatch):
+    cpu_backend.install(monkeypatch)
+    g = golden("pnp.pt")
+    records, per_step = scenarios.run_pnp(g, torch.device("cpu"))
+    _compare(records, per_step, g)
+
+
+def test_pix2pix_zero_processor_reproduces_reference(monkeypatch):
+    cpu_backend.install(monkeypatch)
+    g = golden("pix2pix_zero.pt")
+    out, records, probs, (unet, originals) = scenarios.run_pix2pix_zero(g, torch.device("cpu"))
+    assert (out - g["unet_out"]).abs().max().item() < LAYER_TOL
+    for a, b in zip(records, g["layer_outputs"]):
+        assert (a - b).abs().max().item() < LAYER_TOL
+    assert set(probs) == set(g["cross_probs"]) and len(probs) == 16
+    for name, p in probs.items():
+        assert torch.allclose(p, g["cross_probs"][name], atol=1e-5)
+    from image_editing_framework_b200 import pix2pix_zero
+    pix2pix_zero.restore_original_processors(unet, originals)
+    assert all(type(m.get_processor()).__name__ == "AttnProcessor" for m in unet.modules() if type(m).__name__ == "Attention")
+
+
+def test_p2p_localblend_recomposed_oracle(monkeypatch):
+    """RECOMPOSED oracle (the reference's LocalBlend path crashes as shipped)."""
+    cpu_backend.install(monkeypatch)
+    g = golden("p2p_localblend.pt")
+    ctrl, per_step, maps = scenarios.run_p2p_localblend(g, torch.device("cpu"))
+    for a, b in zip(maps, g["store_16"]):
+        assert torch.allclose(a, b, atol=1e-5)
+    for i, (a, b) in enumerate(zip(per_step, g["latents_per_step"])):
+        assert (a - b).abs().max().item() < 1e-3, f"step {i}"
+
+
+def test_controller_materialised_entry_point_fails_loudly():
+    ctrl = p2p.EmptyControl(False)
+    with pytest.raises(RuntimeError, match="fused"):
+        ctrl(torch.zeros(2, 4, 4), False, "down")
+
+
+def test_attention_mask_is_rejected(monkeypatch):
+    cpu_backend.install(monkeypatch)
+    pipe = make_pipeline(tiny_config(), seed=0)
+    ctrl = p2p.EmptyControl(False)
+    p2p.register_attention_control(pipe, ctrl)
+    attn = pipe.unet.mid_block.attentions[0].transformer_blocks[0].attn1
+    with pytest.raises(NotImplementedError):
+        attn.forward(torch.zeros(1, 4, attn.to_q.in_features), attention_mask=torch.zeros(1, 4))

@@ -9,4 +9,5 @@ run mma "attn_mma or probs_out or rejects"
 run tc "tcgen05 or fp16 or row_sources or masactrl or lazy or auto or strided"
 run cross "cross_attention"
 run elem "ddim or accumulate or local_blend"
+echo "=== e2e"; timeout 900 python -m pytest tests/test_gpu_e2e.py -q -m gpu -p no:cacheprovider --timeout=600 > gpurun_out/t_e2e.log 2>&1; echo "exit $?"; tail -25 gpurun_out/t_e2e.log
 echo "=== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "exit $?"; tail -3 gpurun_out/smoke.log
