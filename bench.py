@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""Headline benchmark: edits/sec @ SD-1.5 512^2, 50 DDIM steps (BASELINE.json metric), workload = configs[1]:
+MasaCtrl mutual self-attention (start step 4, layer 10) with DDIM inversion of a synthetic latent.
+
+One "step" = ONE complete edit of one image:
+    50 inversion UNet forwards (B=1, cond only, fused ddim_reverse) + 50 edit forwards (B=4 = src+tgt x CFG) with the
+    registered MasaCtrl editor (controlled layers -> ief_attn_fwd with per-row K/V sources) + fused CFG/DDIM step.
+The UNet is a random-init stand-in with SD-1.5's full architecture and cost (no weights are available offline); only the
+attention inside it and the step update are this repo's kernels — the rest stays PyTorch, as north_star scopes it.
+
+  python bench.py --gpus N --steps K --warmup W            our arm (one process per GPU under torchrun for N > 1)
+  python bench.py --impl reference ...                     the CPU arm: the reference's materialise-edit-multiply arithmetic
+                                                           (oracle port) on the host cores, bounded sample per step
+
+`value`  : edits/s with the inputs (inverted-image latent + prompt embeddings) already resident in HBM.
+`e2e`    : the same through the public driver with HOST buffers: pinned host -> device copy of the step's inputs and a
+           device -> host read of the edited latents inside the timed region.
+`roofline`: the dominant kernel (tcgen05 controlled self-attention at 64x64 latents: B=4,H=8,N=4096,d=40) timed with CUDA
+           events on the launching stream inside the timed region; algorithmic FLOPs 4*B*H*N*N*d per launch.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "edits/sec @SD1.5 512² 50 DDIM steps; ctrl-attn TFLOP/s vs B200 bf16 peak"
+PROMPTS = ["a photo of a sitting cat", "a photo of a running cat"]
+NUM_STEPS, GUIDANCE, START_STEP, START_LAYER = 50, 7.5, 4, 10
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ddim-steps", type=int, default=NUM_STEPS, help="debug only: anything but 50 is not the headline workload")
+    ap.add_argument("--config", default="sd15", choices=["sd15", "tiny"], help="debug only: 'tiny' is not the headline workload")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        out = {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows else None, "reasons": []}
+        for i, name in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
+            if any(len(r) >= 7 and r[3 + i].lower().startswith("active") for r in self.rows):
+                out["reasons"].append(name)
+        out["samples"] = len(sm)
+        return out
+
+
+# ------------------------------------------------------------------------------------------------ workload
+def build_pipeline(config_name, device, dtype):
+    import torch
+    from image_editing_framework_b200.standin import make_pipeline, sd15_config, tiny_config
+    cfg = sd15_config() if config_name == "sd15" else tiny_config()
+    with torch.device(device):  # random init directly on the target device (860M parameters for sd15)
+        pipe = make_pipeline(cfg, seed=0, device=device, dtype=dtype)
+    return pipe, cfg
+
+
+class KernelTimer:
+    """Wraps ops.attention to bracket the dominant-shape launches with CUDA events on the launching (current) stream."""
+
+    def __init__(self, ops, shape):
+        self.ops, self.shape, self.events, self.inner, self.on = ops, shape, [], ops.attention, False
+
+    def __enter__(self):
+        import torch
+
+        def timed(q, k, v, heads, scale, **kw):
+            if self.on and (q.shape[0], heads, q.shape[1], q.shape[2] // heads) == self.shape and kw.get("probs_out") is None:
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                out = self.inner(q, k, v, heads, scale, **kw)
+                e.record()
+                self.events.append((s, e))
+                return out
+            return self.inner(q, k, v, heads, scale, **kw)
+        self.ops.attention = timed
+        return self
+
+    def __exit__(self, *a):
+        self.ops.attention = self.inner
+
+    def mean_ms(self):
+        ms = [s.elapsed_time(e) for s, e in self.events]
+        return (sum(ms) / len(ms), len(ms)) if ms else (None, 0)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from image_editing_framework_b200 import _cabi, ops, masactrl
+    from image_editing_framework_b200.editing import encode_prompts
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    _cabi.check("ief_check_device", _cabi.lib().ief_check_device())
+    torch.backends.cuda.matmul.allow_tf32 = True
+    pipe, cfg = build_pipeline(args.config, dev, torch.bfloat16)
+    hw = cfg.sample_size
+    regs = (masactrl.regiter_attention_editor_diffusers, masactrl.unregister_attention_control)
+    # inversion runs through the same fused closures with a do-nothing editor registered (plain attention, B=1)
+    plain = masactrl.AttentionBase()
+    context = encode_prompts(pipe, PROMPTS)                      # [uncond, uncond, cond_src, cond_tgt] x 77 x 768, bf16
+    gen = torch.Generator().manual_seed(1234 + rank)
+    host_latent = (torch.randn(1, 4, hw, hw, generator=gen) * 0.18215 * 5).to(torch.bfloat16).pin_memory()  # "VAE-encoded synthetic image"
+    host_context = context.cpu().pin_memory()
+    host_out = torch.empty(2, 4, hw, hw, dtype=torch.bfloat16).pin_memory()
+    dev_latent = host_latent.to(dev)
+
+    def _edit(lat, ctx):
+        import contextlib
+        regs[0](pipe, plain)
+        out = None
+        try:
+            out = _edit_inner(lat, ctx)
+        finally:
+            with contextlib.suppress(Exception):
+                regs[1](pipe, plain)
+        return out
+
+    def _edit_inner(lat, ctx):
+        from image_editing_framework_b200.ddim import FusedDDIM
+        pipe.scheduler.set_timesteps(args.ddim_steps)
+        fused = FusedDDIM(pipe.scheduler)
+        ts = pipe.scheduler.timesteps.tolist()
+        with torch.no_grad():
+            for t in reversed(ts):
+                eps = pipe.unet(lat, t, encoder_hidden_states=ctx[2:3]).sample
+                lat = fused.reverse_step(eps, t, lat)
+            regs[1](pipe, plain)
+            editor = masactrl.MutualSelfAttentionControl(START_STEP, START_LAYER, total_steps=args.ddim_steps)
+            regs[0](pipe, editor)
+            latents = torch.cat([lat, lat])
+            for t in ts:
+                eps = pipe.unet(torch.cat([latents] * 2), t, encoder_hidden_states=ctx).sample
+                latents = fused.step(eps, t, latents, GUIDANCE)
+            regs[1](pipe, editor)
+            regs[0](pipe, plain)
+        return latents
+
+    def edit_from_host():
+        lat = host_latent.to(dev, non_blocking=True)
+        ctx = host_context.to(dev, non_blocking=True)
+        out = _edit(lat, ctx)
+        host_out.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()   # the caller reads the edited latents on the host
+        return host_out
+
+    import io
+    import contextlib as _ctx
+    quiet = _ctx.redirect_stdout(io.StringIO())  # the reference's editor prints its step/layer lists on construction
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = _cabi.launch_count()
+        s.record()
+        for _ in range(k):
+            fn()
+        e.record()
+        barrier()
+        ms = s.elapsed_time(e)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms, _cabi.launch_count() - l0
+
+    dom_shape = (4, 8, hw * hw, cfg.block_out_channels[0] // cfg.num_heads[0])
+    with quiet, KernelTimer(ops, dom_shape) as kt:
+        for _ in range(args.warmup):
+            _edit(dev_latent, context)
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        kt.on = True
+        ms_res, launches = timed(lambda: _edit(dev_latent, context), args.steps)
+        kt.on = False
+        ms_e2e, _ = timed(edit_from_host, args.steps)
+        clocks = sampler.stop() if rank == 0 else None
+    kern_ms, kern_n = kt.mean_ms()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk, pk_src = peaks()
+    B, H, N, d = dom_shape
+    flops = 4.0 * B * H * N * N * d
+    achieved = flops / (kern_ms * 1e-3) / 1e12 if kern_ms else None
+    peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])   # timed inside a long step -> sustained figure
+    line = {
+        "metric": METRIC, "value": round(world * args.steps / (ms_res * 1e-3), 4), "unit": "edits/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms_res / args.steps, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"configs[1]: MasaCtrl mutual self-attention (start step {START_STEP}, layer {START_LAYER}), SD-1.5 512^2, "
+                               f"{args.ddim_steps} DDIM inversion forwards (B=1) + {args.ddim_steps} edit forwards (B=4), guidance {GUIDANCE}",
+                   "unet": f"random-init stand-in with SD-1.5's full architecture ({cfg.name}); attention + step update = libief_b200 kernels, rest PyTorch eager bf16",
+                   "images_per_gpu_per_step": 1, "parallelism": f"image-sharded x{world}, no collective on the hot path",
+                   "l2": "per-forward working set (1.7 GB of weights + activations) exceeds the 126 MB L2; no explicit flush"},
+        "clocks": clocks,
+        "e2e": {"value": round(world * args.steps / (ms_e2e * 1e-3), 4), "unit": "edits/s",
+                "h2d_bytes_per_step": host_latent.numel() * 2 + host_context.numel() * 2, "d2h_bytes_per_step": host_out.numel() * 2},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "kernel": "attn_tc_kernel<bf16> B=4 H=8 N=4096 d=40 (64x64-latent controlled self-attention)",
+                     "achieved": round(achieved, 1) if achieved else None, "peak": peak, "peak_source": f"{pk_src} bf16_tflops_sustained",
+                     "unit": "TFLOP/s", "frac": round(achieved / peak, 4) if achieved else None,
+                     "frac_of_burst_peak": round(achieved / pk["bf16_tflops"], 4) if achieved else None,
+                     "launches_timed": kern_n, "mean_launch_ms": round(kern_ms, 4) if kern_ms else None,
+                     "algorithmic_flops_per_launch": flops, "traffic": TRAFFIC_BYTES_PER_LAUNCH},
+    }
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_sample(args)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from profiles/ (one ncu --set full capture); None until captured
+TRAFFIC_BYTES_PER_LAUNCH = None
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+_CPU_PIPE = {}
+
+
+def cpu_sample(args, reps=1):
+    """Bounded sample of the same workload on the host cores: the reference's arithmetic (materialised fp32 probabilities,
+    oracle port) driven through the same closures. Sample = one inversion forward (B=1) + one controlled edit forward
+    (B=4, step >= 4) of the full-cost UNet; an edit is 50 of each, so edits/s = 1 / (50 * (t_B1 + t_B4))."""
+    import torch
+    from oracle import cpu_ops
+    from image_editing_framework_b200 import masactrl
+    from image_editing_framework_b200.editing import encode_prompts
+    import io
+    import contextlib
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    if args.config not in _CPU_PIPE:
+        _CPU_PIPE[args.config] = build_pipeline(args.config, torch.device("cpu"), torch.float32)
+    pipe, cfg = _CPU_PIPE[args.config]
+    hw = cfg.sample_size
+    context = encode_prompts(pipe, PROMPTS)
+    lat = torch.randn(1, 4, hw, hw, generator=torch.Generator().manual_seed(1))
+    pipe.scheduler.set_timesteps(args.ddim_steps)
+    t_mid = pipe.scheduler.timesteps.tolist()[len(pipe.scheduler.timesteps) // 2]
+    times = []
+    with cpu_ops.patched(), torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+        for _ in range(reps):
+            plain = masactrl.AttentionBase()
+            masactrl.regiter_attention_editor_diffusers(pipe, plain)
+            t0 = time.perf_counter()
+            pipe.unet(lat, t_mid, encoder_hidden_states=context[2:3])
+            t1 = time.perf_counter()
+            masactrl.unregister_attention_control(pipe, plain)
+            ed = masactrl.MutualSelfAttentionControl(START_STEP, START_LAYER, total_steps=args.ddim_steps)
+            masactrl.regiter_attention_editor_diffusers(pipe, ed)
+            ed.cur_step = max(START_STEP, args.ddim_steps // 2)
+            t2 = time.perf_counter()
+            pipe.unet(torch.cat([lat] * 4), t_mid, encoder_hidden_states=context)
+            t3 = time.perf_counter()
+            masactrl.unregister_attention_control(pipe, ed)
+            times.append((t1 - t0, t3 - t2))
+    t_b1 = min(t[0] for t in times)
+    t_b4 = min(t[1] for t in times)
+    return {"value": round(1.0 / (args.ddim_steps * (t_b1 + t_b4)), 6), "unit": "edits/s", "cores": cores, "kind": "port",
+            "sample": f"1 inversion UNet forward (B=1, {t_b1:.2f} s) + 1 MasaCtrl-controlled edit forward (B=4, {t_b4:.2f} s), fp32, torch on {cores} threads; "
+                      f"extrapolated x{args.ddim_steps} each"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t0 = time.perf_counter()
+    samples = []
+    for i in range(args.warmup + args.steps):
+        s = cpu_sample(args)
+        if i >= args.warmup:
+            samples.append(s)
+        if time.perf_counter() - t0 > 240 and len(samples) >= 1:   # keep the whole arm within a few minutes
+            break
+    v = statistics.median(s["value"] for s in samples)
+    base = dict(samples[-1])
+    base["value"] = v
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "edits/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+            "steps": len(samples), "warmup": args.warmup, "ms_per_step": round(1e3 / v, 1), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"configs[1]: MasaCtrl mutual self-attention, SD-1.5 512^2, {args.ddim_steps}+{args.ddim_steps} UNet forwards; bounded CPU sample per step"},
+            "cpu_baseline": base, "e2e": {"value": v, "unit": "edits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -1,8 +1,12 @@
-"""TEST-ONLY stand-ins for image_editing_framework_b200.ops built from the CPU oracle.
+"""Oracle-backed CPU stand-ins for image_editing_framework_b200.ops — TEST / BASELINE INFRASTRUCTURE ONLY.
 
 They let `-m "not gpu"` tests drive the real host logic (register closures, controller state machines, row tables, store
-bookkeeping, drivers) on a CPU and compare it with the golden vectors. The product never imports this module.
+bookkeeping, drivers) on a CPU against the golden vectors, and they are what bench.py's `cpu_baseline` / `--impl reference`
+legs time: the reference's materialise-edit-multiply arithmetic (oracle/controlled_attention.py) in fp32 on the host cores.
+The product never imports this module; it is installed by explicit patching only (install / patched).
 """
+import contextlib
+
 import torch
 
 from oracle import controlled_attention as orc
@@ -95,8 +99,29 @@ def cfg_ddim_step(eps_uncond, eps_cond, x, guidance, alpha_t, alpha_prev, out=No
     return orc.ddim_step(eps, x, torch.tensor(alpha_t, dtype=torch.float32), torch.tensor(alpha_prev, dtype=torch.float32)).to(x.dtype)
 
 
+_NAMES = ("attention", "cross_attention_edit", "store_accumulate", "local_blend", "cfg_ddim_step")
+
+
 def install(monkeypatch):
+    """pytest flavour: undone automatically at test teardown."""
     from image_editing_framework_b200 import hooks
-    monkeypatch.setattr(hooks, "compute_dtype", lambda t: t.dtype)  # keep fp32: these tests isolate host logic from bf16 rounding
-    for name in ("attention", "cross_attention_edit", "store_accumulate", "local_blend", "cfg_ddim_step"):
+    monkeypatch.setattr(hooks, "compute_dtype", lambda t: t.dtype)  # keep fp32: isolates host logic from bf16 rounding
+    for name in _NAMES:
         monkeypatch.setattr(real_ops, name, globals()[name])
+
+
+@contextlib.contextmanager
+def patched():
+    """bench.py flavour: route the host logic to the CPU oracle inside the `with` block only."""
+    from image_editing_framework_b200 import hooks
+    saved = {n: getattr(real_ops, n) for n in _NAMES}
+    saved_dt = hooks.compute_dtype
+    try:
+        hooks.compute_dtype = lambda t: t.dtype
+        for n in _NAMES:
+            setattr(real_ops, n, globals()[n])
+        yield
+    finally:
+        hooks.compute_dtype = saved_dt
+        for n, f in saved.items():
+            setattr(real_ops, n, f)

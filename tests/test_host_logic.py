@@ -1,5 +1,5 @@
 """CPU suite: goldens produced by the reference's own code pin (a) the bit-exact host-side integer logic, (b) the oracle,
-(c) the controller / register / driver host logic (driven here through oracle-backed fake ops, see tests/cpu_backend.py)."""
+(c) the controller / register / driver host logic (driven here through oracle-backed fake ops, see oracle/cpu_ops.py)."""
 import os
 import re
 
@@ -13,7 +13,7 @@ from image_editing_framework_b200.standin import WordPieceTokenizer, make_pipeli
 from oracle import controlled_attention as orc
 from oracle import reference_loader
 
-import cpu_backend
+from oracle import cpu_ops as cpu_backend
 import scenarios
 from scenarios import golden
 
