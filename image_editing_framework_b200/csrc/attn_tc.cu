@@ -15,6 +15,7 @@
 // Two CTAs are resident per SM for head_dim <= 64, so one CTA's exp work overlaps the other's MMAs.
 #include "ief_common.cuh"
 #include "ptx_sm100.cuh"
+#include "attn_tc_host.cuh"
 #include <cuda.h>
 #include <stdlib.h>
 #include <math.h>
@@ -25,23 +26,10 @@ namespace {
 
 constexpr int kBM = 128;          // query rows per CTA
 constexpr int kBN = 128;          // keys per KV tile
-constexpr int kChunkBytes = kBN * 128;  // one [128 rows x 64 elem] swizzled box = 16 KiB
+constexpr int kChunkBytes = kTcChunkBytes;
 constexpr int kThreads = 192;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units: P may grow to 2^8 before O is rescaled
-
-struct TcArgs {
-  void* o;
-  int64_t o_sb, o_sn, o_sh;
-  int32_t B, H, Nq, Nk, d;
-  int32_t nt1, nt2;        // KV tiles in block 1 / block 2 (Union)
-  int32_t ksteps_qk;       // ceil(d/16)
-  int32_t dv_mma;          // N of the PV MMA (>= d, multiple of 16)
-  uint32_t idesc_qk, idesc_pv;
-  float scale_log2;
-  int32_t perm_q[3], perm_k[3], perm_v[3];  // which of (token, head, row) feeds TMA coordinate 1..3
-  IefRowTable rows;
-};
 
 template <int DCH> struct TcCfg {
   static constexpr int kStages = (DCH == 3) ? 1 : 2;
@@ -52,10 +40,7 @@ template <int DCH> struct TcCfg {
   static constexpr int kMinBlocks = (DCH == 1) ? 2 : 1;
 };
 
-__device__ __forceinline__ void tma_tile(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int tok, int head, int row, const int32_t (&perm)[3]) {
-  int cc[3] = {tok, head, row};
-  tma_load_4d(dst, m, bar, c0, cc[perm[0]], cc[perm[1]], cc[perm[2]]);
-}
+#define tma_tile tc_tma_tile
 
 template <int DTYPE, int DCH>
 __global__ void __launch_bounds__(kThreads, TcCfg<DCH>::kMinBlocks)
@@ -377,11 +362,15 @@ int ief_attn_tc_launch(const ief_attn_params* p, const IefRowTable& rows, cudaSt
   a.idesc_pv = make_idesc_f16(kBM, a.dv_mma, fmt, 0, 1);
   a.scale_log2 = p->scale * kLog2e;
   a.rows = rows;
+  a.dbg = ief_debug_trace_buffer();
   CUtensorMap mq, mk, mv;
   int rc;
   if ((rc = make_map(&mq, p->dtype, p->q, p->d, p->Nq, p->H, p->B, a.perm_q)) != IEF_OK) return rc;
   if ((rc = make_map(&mk, p->dtype, p->k, p->d, p->Nk, p->H, p->B, a.perm_k)) != IEF_OK) return rc;
   if ((rc = make_map(&mv, p->dtype, p->v, p->d, p->Nk, p->H, p->B, a.perm_v)) != IEF_OK) return rc;
+  static int version = -1;  // IEF_TC_VERSION=1 forces the first-generation kernel (A/B measurements); default: v2 when head_dim <= 128
+  if (version < 0) { const char* e = getenv("IEF_TC_VERSION"); version = (e && e[0] == '1') ? 1 : 2; }
+  if (version == 2 && dch <= 2) return ief_attn_tc2_launch(p, mq, mk, mv, a, st);
   dim3 grid(ief_ceil_div(p->Nq, kBM), p->H, p->B);
   if (p->dtype == IEF_BF16) {
     if (dch == 1) return launch_tc<IEF_BF16, 1>(mq, mk, mv, a, grid, st);

@@ -1,0 +1,30 @@
+// Definitions shared by the two tcgen05 attention kernels (attn_tc.cu, attn_tc2.cu).
+#pragma once
+#include "ief_common.cuh"
+#include "ptx_sm100.cuh"
+#include <cuda.h>
+
+constexpr int kTcChunkBytes = 128 * 128;  // one [128 rows x 64 elem] SWIZZLE_128B box = 16 KiB
+
+struct TcArgs {
+  void* o;
+  int64_t o_sb, o_sn, o_sh;
+  int32_t B, H, Nq, Nk, d;
+  int32_t nt1, nt2;        // KV tiles in block 1 / block 2 (Union)
+  int32_t ksteps_qk;       // ceil(d/16)
+  int32_t dv_mma;          // N of the PV MMA (>= d, multiple of 16)
+  uint32_t idesc_qk, idesc_pv;
+  float scale_log2;
+  int32_t perm_q[3], perm_k[3], perm_v[3];  // which of (token, head, row) feeds TMA coordinate 1..3
+  IefRowTable rows;
+  long long* dbg;  // optional clock64 trace of CTA (0,0,0), see ief_debug_set_trace_buffer
+};
+
+__device__ __forceinline__ void tc_tma_tile(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int tok, int head, int row,
+                                            const int32_t (&perm)[3]) {
+  int cc[3] = {tok, head, row};
+  sm100::tma_load_4d(dst, m, bar, c0, cc[perm[0]], cc[perm[1]], cc[perm[2]]);
+}
+
+long long* ief_debug_trace_buffer();
+int ief_attn_tc2_launch(const ief_attn_params* p, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const TcArgs& a, cudaStream_t st);

@@ -1,0 +1,38 @@
+"""Per-phase clock64 trace of CTA (0,0,0) of the v2 tcgen05 attention kernel (debug hook ief_debug_set_trace_buffer)."""
+import ctypes as C
+import os
+import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from image_editing_framework_b200 import ops, _cabi
+
+B, H, N, d = (int(x) for x in (sys.argv[1:5] if len(sys.argv) >= 5 else (4, 8, 4096, 40)))
+dev = torch.device("cuda:0")
+q, k, v = (torch.randn(B, N, H * d, device=dev).to(torch.bfloat16) for _ in range(3))
+buf = torch.zeros(2048, dtype=torch.int64, device=dev)
+lib = _cabi.lib()
+lib.ief_debug_set_trace_buffer.argtypes = [C.c_void_p]
+for _ in range(3):
+    ops.attention(q, k, v, H, d ** -0.5, impl=ops.IEF_IMPL_TCGEN05)
+lib.ief_debug_set_trace_buffer(buf.data_ptr())
+ops.attention(q, k, v, H, d ** -0.5, impl=ops.IEF_IMPL_TCGEN05)
+torch.cuda.synchronize()
+lib.ief_debug_set_trace_buffer(None)
+t = buf.cpu()
+sm = t[:1024].view(2, 64, 8)
+mm = t[1024:1536].view(2, 64, 4)
+t0 = int(sm[0, 0, 0])
+nt = min(N // 128, 64)
+print("softmax WG phases (cycles): wait_S | ld | max | exp+st-issue | wait_st+arrive   || tile period")
+for wg in range(2):
+    for j in range(2, min(nt, 14)):
+        r = sm[wg, j]
+        period = int(sm[wg, j, 0] - sm[wg, j - 1, 0])
+        print(f"wg{wg} j={j:2d} start={int(r[0]) - t0:7d}  wait_S={int(r[1] - r[0]):5d} ld={int(r[2] - r[1]):4d} max={int(r[3] - r[2]):4d} exp={int(r[4] - r[3]):5d} st+arr={int(r[5] - r[4]):4d} | period={period}")
+print("MMA warp: wait_P(+K) | issue PV+QK+commits")
+for tt in range(2):
+    for j in range(2, min(nt - 1, 14)):
+        r = mm[tt, j]
+        print(f"t{tt} j={j:2d} at={int(r[0]) - t0:7d} wait_P={int(r[1] - r[0]):5d} issue={int(r[3] - r[1]):4d}")
+tot = int(sm[0, nt - 1, 5] - sm[0, 0, 0])
+print(f"total cycles for {nt} tiles (wg0): {tot}  -> {tot / nt:.0f} per tile-pair")
