@@ -254,7 +254,7 @@ def run_ours(args):
         "e2e": {"value": round(world * args.steps / (ms_e2e * 1e-3), 4), "unit": "edits/s",
                 "h2d_bytes_per_step": host_latent.numel() * 2 + host_context.numel() * 2, "d2h_bytes_per_step": host_out.numel() * 2},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "kernel": "attn_tc_kernel<bf16> B=4 H=8 N=4096 d=40 (64x64-latent controlled self-attention)",
+        "roofline": {"bound": "tensor", "kernel": "attn_tc2_kernel<bf16,d<=64> B=4 H=8 N=4096 d=40 (64x64-latent controlled self-attention)",
                      "achieved": round(achieved, 1) if achieved else None, "peak": peak, "peak_source": f"{pk_src} bf16_tflops_sustained",
                      "unit": "TFLOP/s", "frac": round(achieved / peak, 4) if achieved else None,
                      "frac_of_burst_peak": round(achieved / pk["bf16_tflops"], 4) if achieved else None,
@@ -269,7 +269,7 @@ def run_ours(args):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from profiles/ (one ncu --set full capture); None until captured
-TRAFFIC_BYTES_PER_LAUNCH = None
+TRAFFIC_BYTES_PER_LAUNCH = 21.02e6  # profiles/r01_attn_tc2_sd15_64_ncu_full.txt (read 21.02 MB + write 1 KB)
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm

@@ -330,16 +330,20 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mask_chunk(s3, 96, vc);
       }
       const float tmax = fmaxf(fmaxf(max_chunk(s0, -INFINITY), max_chunk(s1, -INFINITY)), fmaxf(max_chunk(s2, -INFINITY), max_chunk(s3, -INFINITY)));
+      // PV_t(j-1) must be complete before P_t is rewritten or O_t rescaled (split-P layout). The wait is deferred
+      // until the first chunk of exponentials has been computed, unless a rescale needs O earlier.
+      bool o_ready = !Cfg::kSplitP || j == 0;
       if (j == 0) {
         m_used = tmax;
       } else {
-        if constexpr (Cfg::kSplitP) {  // PV_t(j-1) must be done before P_t is rewritten or O_t rescaled
-          mbar_wait(bar_o(t), (j - 1) & 1);
-          tc_fence_after();
-        }
         const float m_new = fmaxf(m_used, tmax);
         const bool need = (m_new - m_used) * c2 > kRescaleThreshold;
         if (__any_sync(0xffffffffu, need)) {
+          if (!o_ready) {
+            mbar_wait(bar_o(t), (j - 1) & 1);
+            tc_fence_after();
+            o_ready = true;
+          }
           const float alpha = ief_exp2((m_used - m_new) * c2);
           for (int cc = 0; cc < nchunk_o; ++cc) {
             uint32_t r[16];
@@ -359,6 +363,10 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
       uint32_t u[16];
       exp_chunk<E>(s0, u, c2v, nmc, acc0, acc1);
+      if (!o_ready) {
+        mbar_wait(bar_o(t), (j - 1) & 1);
+        tc_fence_after();
+      }
       tmem_st16(tP, u);
       exp_chunk<E>(s1, u, c2v, nmc, acc0, acc1);
       tmem_st16(tP + 16, u);
