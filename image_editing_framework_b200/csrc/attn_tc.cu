@@ -363,14 +363,19 @@ int ief_attn_tc_launch(const ief_attn_params* p, const IefRowTable& rows, cudaSt
   a.scale_log2 = p->scale * kLog2e;
   a.rows = rows;
   a.dbg = ief_debug_trace_buffer();
+  static int skew = -1;
+  if (skew < 0) { const char* e = getenv("IEF_TC_SKEW"); skew = e ? atoi(e) : 1300; }
+  a.skew_cycles = skew;
   CUtensorMap mq, mk, mv;
   int rc;
   if ((rc = make_map(&mq, p->dtype, p->q, p->d, p->Nq, p->H, p->B, a.perm_q)) != IEF_OK) return rc;
   if ((rc = make_map(&mk, p->dtype, p->k, p->d, p->Nk, p->H, p->B, a.perm_k)) != IEF_OK) return rc;
   if ((rc = make_map(&mv, p->dtype, p->v, p->d, p->Nk, p->H, p->B, a.perm_v)) != IEF_OK) return rc;
-  static int version = -1;  // IEF_TC_VERSION=1 forces the first-generation kernel (A/B measurements); default: v2 when head_dim <= 128
-  if (version < 0) { const char* e = getenv("IEF_TC_VERSION"); version = (e && e[0] == '1') ? 1 : 2; }
-  if (version == 2 && dch <= 2) return ief_attn_tc2_launch(p, mq, mk, mv, a, st);
+  // default: third generation for head_dim <= 64, second for 65..128, first above. IEF_TC_VERSION=1|2|3 caps the generation (A/B measurements).
+  static int version = -1;
+  if (version < 0) { const char* e = getenv("IEF_TC_VERSION"); version = (e && e[0] >= '1' && e[0] <= '3') ? e[0] - '0' : 3; }
+  if (version >= 3 && dch == 1) return ief_attn_tc3_launch(p, mq, mk, mv, a, st);
+  if (version >= 2 && dch <= 2) return ief_attn_tc2_launch(p, mq, mk, mv, a, st);
   dim3 grid(ief_ceil_div(p->Nq, kBM), p->H, p->B);
   if (p->dtype == IEF_BF16) {
     if (dch == 1) return launch_tc<IEF_BF16, 1>(mq, mk, mv, a, grid, st);

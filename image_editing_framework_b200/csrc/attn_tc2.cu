@@ -27,6 +27,7 @@
 #include "ief_common.cuh"
 #include "ptx_sm100.cuh"
 #include "attn_tc_host.cuh"
+#include "attn_tc_dev.cuh"
 #include <math.h>
 
 using namespace sm100;
@@ -52,62 +53,6 @@ template <int DCH> struct Cfg2 {
   static constexpr int kStrideO = kSplitP ? 64 : 128;
 };
 
-template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
-template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
-
-__device__ __forceinline__ float fmax3(float a, float b, float c) {
-  float r;
-  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
-  return r;
-}
-__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
-  float2 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;"
-      : "=l"(reinterpret_cast<uint64_t&>(d))
-      : "l"(reinterpret_cast<const uint64_t&>(a)), "l"(reinterpret_cast<const uint64_t&>(b)), "l"(reinterpret_cast<const uint64_t&>(c)));
-  return d;
-}
-__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
-  float2 d;
-  asm("add.rn.f32x2 %0, %1, %2;"
-      : "=l"(reinterpret_cast<uint64_t&>(d))
-      : "l"(reinterpret_cast<const uint64_t&>(a)), "l"(reinterpret_cast<const uint64_t&>(b)));
-  return d;
-}
-
-// one 32-column chunk of scores -> probabilities (packed 16-bit pairs), accumulating the fp32 row sum
-template <typename E>
-__device__ __forceinline__ void exp_chunk(const uint32_t (&s)[32], uint32_t (&u)[16], float2 c2, float2 nmc, float2& acc0, float2& acc1) {
-#pragma unroll
-  for (int i = 0; i < 16; i += 2) {
-    float2 x0 = ffma2(make_float2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])), c2, nmc);
-    float2 x1 = ffma2(make_float2(__uint_as_float(s[2 * i + 2]), __uint_as_float(s[2 * i + 3])), c2, nmc);
-    x0.x = ief_exp2(x0.x); x0.y = ief_exp2(x0.y);
-    x1.x = ief_exp2(x1.x); x1.y = ief_exp2(x1.y);
-    acc0 = fadd2(acc0, x0);
-    acc1 = fadd2(acc1, x1);
-    u[i] = E::pack(x0.x, x0.y);
-    u[i + 1] = E::pack(x1.x, x1.y);
-  }
-}
-
-__device__ __forceinline__ float max_chunk(const uint32_t (&s)[32], float m) {
-  float m0 = m, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-#pragma unroll
-  for (int i = 0; i < 32; i += 8) {
-    m0 = fmax3(m0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
-    m1 = fmax3(m1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
-    m2 = fmax3(m2, __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
-    m3 = fmax3(m3, __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
-  }
-  return fmaxf(fmax3(m0, m1, m2), m3);
-}
-
-__device__ __forceinline__ void mask_chunk(uint32_t (&s)[32], int col0, int vc) {
-#pragma unroll
-  for (int i = 0; i < 32; ++i)
-    if (col0 + i >= vc) s[i] = 0xff800000u;  // -inf
-}
 
 template <int DTYPE, int DCH>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -300,6 +245,10 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const float c2 = a.scale_log2;
     float m_used = -INFINITY, l = 0.f;
     const int nchunk_o = a.dv_mma >> 4;
+    if (t == 1 && a.skew_cycles > 0) {  // de-phase the two tiles once: in lock-step their exp phases collide and the MUFU idles in between
+      const long long t0 = clock64();
+      while (clock64() - t0 < a.skew_cycles) {}
+    }
 
     for (int j = 0; j < nt; ++j) {
       const bool blk2 = j >= a.nt1;

@@ -17,6 +17,7 @@ struct TcArgs {
   float scale_log2;
   int32_t perm_q[3], perm_k[3], perm_v[3];  // which of (token, head, row) feeds TMA coordinate 1..3
   IefRowTable rows;
+  int32_t skew_cycles;  // one-time start delay of query tile B's softmax warps (keeps the two tiles' exp phases out of step)
   long long* dbg;  // optional clock64 trace of CTA (0,0,0), see ief_debug_set_trace_buffer
 };
 
@@ -27,4 +28,5 @@ __device__ __forceinline__ void tc_tma_tile(uint32_t dst, const CUtensorMap* m, 
 }
 
 long long* ief_debug_trace_buffer();
+int ief_attn_tc3_launch(const ief_attn_params* p, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const TcArgs& a, cudaStream_t st);
 int ief_attn_tc2_launch(const ief_attn_params* p, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const TcArgs& a, cudaStream_t st);

@@ -46,6 +46,18 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "memory");
   return done;
 }
+// Non-blocking probe (does not suspend the thread), used by the event-driven MMA issue loop.
+__device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done;
+}
 // Bounded wait: a protocol bug must trap (surfacing as a CUDA error) instead of hanging the GPU box.
 #ifndef IEF_MBAR_TIMEOUT_CYCLES
 #define IEF_MBAR_TIMEOUT_CYCLES 6000000000ll  // ~3 s at 1.9 GHz

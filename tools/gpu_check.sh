@@ -7,6 +7,8 @@ run() { name=$1; shift; echo "=== $name" ; timeout 600 python -m pytest tests/te
 run probe "umma_probe"
 run mma "attn_mma or probs_out or rejects"
 run tc "tcgen05 or fp16 or row_sources or masactrl or lazy or auto or strided"
+IEF_TC_VERSION=2 run tc_v2 "tcgen05 or fp16 or row_sources or masactrl or lazy or strided"
+IEF_TC_VERSION=1 run tc_v1 "tcgen05 or fp16 or row_sources or masactrl or lazy or strided"
 run cross "cross_attention"
 run elem "ddim or accumulate or local_blend"
 echo "=== e2e"; timeout 900 python -m pytest tests/test_gpu_e2e.py -q -m gpu -p no:cacheprovider --timeout=600 > gpurun_out/t_e2e.log 2>&1; echo "exit $?"; tail -25 gpurun_out/t_e2e.log

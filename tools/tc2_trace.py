@@ -29,6 +29,8 @@ for wg in range(2):
         r = sm[wg, j]
         period = int(sm[wg, j, 0] - sm[wg, j - 1, 0])
         print(f"wg{wg} j={j:2d} start={int(r[0]) - t0:7d}  wait_S={int(r[1] - r[0]):5d} ld={int(r[2] - r[1]):4d} max={int(r[3] - r[2]):4d} exp={int(r[4] - r[3]):5d} st+arr={int(r[5] - r[4]):4d} | period={period}")
+print("offset wg1.start - wg0.start per tile:", [int(sm[1, j, 0] - sm[0, j, 0]) for j in range(0, nt)])
+print("exp start wg0/wg1 rel:", [(int(sm[0, j, 3]) - t0, int(sm[1, j, 3]) - t0) for j in range(0, min(nt, 8))])
 print("MMA warp: wait_P(+K) | issue PV+QK+commits")
 for tt in range(2):
     for j in range(2, min(nt - 1, 14)):
