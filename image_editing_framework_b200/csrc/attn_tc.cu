@@ -373,8 +373,28 @@ int ief_attn_tc_launch(const ief_attn_params* p, const IefRowTable& rows, cudaSt
   if ((rc = make_map(&mv, p->dtype, p->v, p->d, p->Nk, p->H, p->B, a.perm_v)) != IEF_OK) return rc;
   // default: third generation for head_dim <= 64, second for 65..128, first above. IEF_TC_VERSION=1|2|3 caps the generation (A/B measurements).
   static int version = -1;
-  if (version < 0) { const char* e = getenv("IEF_TC_VERSION"); version = (e && e[0] >= '1' && e[0] <= '3') ? e[0] - '0' : 3; }
+  if (version < 0) { const char* e = getenv("IEF_TC_VERSION"); version = (e && e[0] >= '1' && e[0] <= '3') ? e[0] - '0' : 2; }
   if (version >= 3 && dch == 1) return ief_attn_tc3_launch(p, mq, mk, mv, a, st);
+  if (version >= 2 && dch == 1) {
+    // 256-row CTAs (two query tiles share K/V) or 128-row CTAs (two key halves share Q)? Estimated time = waves x (key steps
+    // per CTA + fixed prologue/epilogue, about three steps' worth): take the smaller. IEF_TC_SPLITKV=0|1 forces the choice.
+    static int force = -2, sms = 0;
+    if (force == -2) {
+      const char* e = getenv("IEF_TC_SPLITKV");
+      force = e ? atoi(e) : -1;
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      if (sms <= 0) sms = 148;
+    }
+    int active = 0;
+    for (int i = 0; i < p->B; ++i) active += rows.active[i] ? 1 : 0;
+    const int nt = a.nt1 + a.nt2;
+    const long n_pair = (long)ief_ceil_div(p->Nq, 2 * kBM) * p->H * active, n_split = (long)ief_ceil_div(p->Nq, kBM) * p->H * active;
+    const long t_pair = ((n_pair + sms - 1) / sms) * (nt + 3), t_split = ((n_split + sms - 1) / sms) * ((nt + 1) / 2 + 3);
+    const bool split = force >= 0 ? force != 0 : t_split < t_pair;
+    if (split) return ief_attn_tc2s_launch(p, mq, mk, mv, a, st);
+  }
   if (version >= 2 && dch <= 2) return ief_attn_tc2_launch(p, mq, mk, mv, a, st);
   dim3 grid(ief_ceil_div(p->Nq, kBM), p->H, p->B);
   if (p->dtype == IEF_BF16) {

@@ -29,4 +29,5 @@ __device__ __forceinline__ void tc_tma_tile(uint32_t dst, const CUtensorMap* m, 
 
 long long* ief_debug_trace_buffer();
 int ief_attn_tc3_launch(const ief_attn_params* p, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const TcArgs& a, cudaStream_t st);
+int ief_attn_tc2s_launch(const ief_attn_params* p, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const TcArgs& a, cudaStream_t st);
 int ief_attn_tc2_launch(const ief_attn_params* p, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const TcArgs& a, cudaStream_t st);

@@ -8,7 +8,7 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompil
 objs=()
 pids=()
 mkdir -p "$here/build"
-for f in api attn_tc attn_tc2 attn_tc3 attn_mma cross_attn elementwise; do
+for f in api attn_tc attn_tc2 attn_tc2s attn_tc3 attn_mma cross_attn elementwise; do
   "$NVCC" "${FLAGS[@]}" -c "$here/$f.cu" -o "$here/build/$f.o" &
   pids+=($!)
   objs+=("$here/build/$f.o")
