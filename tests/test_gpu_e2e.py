@@ -116,3 +116,35 @@ def test_fused_ddim_inversion_loop_matches_reference_formula(cuda):
     for t, want in g["forward"].items():
         got = fused.step(torch.cat([eu, ec]).to(cuda), t, xx.to(cuda), g["guidance"]).cpu()
         assert torch.equal(got, want), f"t={t}: {(got - want).abs().max().item()}"
+
+
+def test_cuda_graph_replay_equals_eager(cuda):
+    """The fused attention launches are captured like torch ops (tensor maps / row tables travel by value)."""
+    import io
+    from contextlib import redirect_stdout
+    from image_editing_framework_b200 import masactrl, editing
+    from image_editing_framework_b200.graphs import GraphedCall
+    from image_editing_framework_b200.standin import make_pipeline, tiny_config
+    from image_editing_framework_b200.standin.unet import UNetConfig
+    cfg = UNetConfig(sample_size=32, block_out_channels=(64, 128, 128, 128), num_heads=(2, 2, 2, 2), cross_attention_dim=32, norm_num_groups=8, name="g")
+    pipe = make_pipeline(cfg, seed=0, device=cuda, dtype=torch.bfloat16)
+    ctx = editing.encode_prompts(pipe, ["a cat", "a dog"])
+    with redirect_stdout(io.StringIO()):
+        ed = masactrl.MutualSelfAttentionControl(0, 10, total_steps=4)
+    masactrl.regiter_attention_editor_diffusers(pipe, ed)
+
+    def fwd(x, t, c):
+        ed.cur_step, ed.cur_att_layer = 1, 0
+        return pipe.unet(x, t, encoder_hidden_states=c).sample
+
+    x = torch.randn(4, 4, 32, 32, device=cuda, dtype=torch.bfloat16)   # 32x32 latents: 1024-token layers run the tcgen05 kernel
+    t = torch.tensor(501, device=cuda)
+    with torch.no_grad():
+        want = fwd(x, t, ctx).clone()
+    g = GraphedCall(fwd, [x, t, ctx], launch_counter=_cabi.launch_count)
+    assert g.captured_launches == 32
+    x2 = torch.randn_like(x)
+    with torch.no_grad():
+        want2 = fwd(x2, t, ctx).clone()
+    assert torch.equal(g(x, t, ctx), want)
+    assert torch.equal(g(x2, t, ctx), want2)
