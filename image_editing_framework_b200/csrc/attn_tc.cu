@@ -364,17 +364,19 @@ int ief_attn_tc_launch(const ief_attn_params* p, const IefRowTable& rows, cudaSt
   a.rows = rows;
   a.dbg = ief_debug_trace_buffer();
   static int skew = -1;
-  if (skew < 0) { const char* e = getenv("IEF_TC_SKEW"); skew = e ? atoi(e) : 1300; }
+  if (skew < 0) { const char* e = getenv("IEF_TC_SKEW"); skew = e ? atoi(e) : 1; }
   a.skew_cycles = skew;
   CUtensorMap mq, mk, mv;
   int rc;
   if ((rc = make_map(&mq, p->dtype, p->q, p->d, p->Nq, p->H, p->B, a.perm_q)) != IEF_OK) return rc;
   if ((rc = make_map(&mk, p->dtype, p->k, p->d, p->Nk, p->H, p->B, a.perm_k)) != IEF_OK) return rc;
   if ((rc = make_map(&mv, p->dtype, p->v, p->d, p->Nk, p->H, p->B, a.perm_v)) != IEF_OK) return rc;
-  // default: third generation for head_dim <= 64, second for 65..128, first above. IEF_TC_VERSION=1|2|3 caps the generation (A/B measurements).
+  // Kernel generations (IEF_TC_VERSION=1|2|3 caps the generation for A/B measurements):
+  //   head_dim <= 64 : 128-row split-KV CTAs (attn_tc2s) when that shortens the estimated wave time, else the third generation
+  //                    (attn_tc3: 256-row CTAs, column-split softmax, ordered exp sections)
+  //   head_dim <= 128: second generation (attn_tc2, P aliased onto S)        above: first generation (this file)
   static int version = -1;
-  if (version < 0) { const char* e = getenv("IEF_TC_VERSION"); version = (e && e[0] >= '1' && e[0] <= '3') ? e[0] - '0' : 2; }
-  if (version >= 3 && dch == 1) return ief_attn_tc3_launch(p, mq, mk, mv, a, st);
+  if (version < 0) { const char* e = getenv("IEF_TC_VERSION"); version = (e && e[0] >= '1' && e[0] <= '3') ? e[0] - '0' : 3; }
   if (version >= 2 && dch == 1) {
     // 256-row CTAs (two query tiles share K/V) or 128-row CTAs (two key halves share Q)? Estimated time = waves x (key steps
     // per CTA + fixed prologue/epilogue, about three steps' worth): take the smaller. IEF_TC_SPLITKV=0|1 forces the choice.
@@ -394,6 +396,7 @@ int ief_attn_tc_launch(const ief_attn_params* p, const IefRowTable& rows, cudaSt
     const long t_pair = ((n_pair + sms - 1) / sms) * (nt + 3), t_split = ((n_split + sms - 1) / sms) * ((nt + 1) / 2 + 3);
     const bool split = force >= 0 ? force != 0 : t_split < t_pair;
     if (split) return ief_attn_tc2s_launch(p, mq, mk, mv, a, st);
+    if (version >= 3) return ief_attn_tc3_launch(p, mq, mk, mv, a, st);
   }
   if (version >= 2 && dch <= 2) return ief_attn_tc2_launch(p, mq, mk, mv, a, st);
   dim3 grid(ief_ceil_div(p->Nq, kBM), p->H, p->B);

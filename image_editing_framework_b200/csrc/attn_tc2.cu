@@ -245,11 +245,6 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const float c2 = a.scale_log2;
     float m_used = -INFINITY, l = 0.f;
     const int nchunk_o = a.dv_mma >> 4;
-    if (t == 1 && a.skew_cycles > 0) {  // de-phase the two tiles once: in lock-step their exp phases collide and the MUFU idles in between
-      const long long t0 = clock64();
-      while (clock64() - t0 < a.skew_cycles) {}
-    }
-
     for (int j = 0; j < nt; ++j) {
       const bool blk2 = j >= a.nt1;
       const int jj = blk2 ? j - a.nt1 : j;

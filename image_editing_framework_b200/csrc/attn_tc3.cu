@@ -253,23 +253,28 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // Ordered exp sections (the ping-pong of FlashAttention-3/4): tile A's and tile B's exponentials strictly alternate,
       // so each runs on an uncontended MUFU while the other tile loads / reduces / synchronises. Left to themselves the two
       // tiles fall into lock-step (both idle the MUFU during their non-exp phases, then share it).
-      if (a.skew_cycles != 0 && (t == 1 || j > 0)) mbar_wait(bar_x(t), (t == 1 ? j : j - 1) & 1);
-      if (trace) tr[3] = clock64();
       const float mc = m_used * c2;
       const float2 c2v = make_float2(c2, c2), nmc = make_float2(-mc, -mc);
-      float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
-      uint32_t u[16];
-      exp_chunk<E>(s0, u, c2v, nmc, acc0, acc1);
-      if (!o_ready) {  // PV_t(j-1) must have finished reading P_t before it is overwritten
+      scale_chunk(s0, c2v, nmc);   // FMA pipe work, outside the MUFU turn
+      scale_chunk(s1, c2v, nmc);
+      if (!o_ready) {  // PV_t(j-1) must have finished reading P_t; wait for it BEFORE taking the exp turn, not inside it
         mbar_wait(bar_o(t), (j - 1) & 1);
         tc_fence_after();
+        o_ready = true;
       }
+      // Ordered exp sections (the ping-pong of FlashAttention-3/4): tile A's and tile B's exponentials strictly alternate,
+      // so each runs on an uncontended MUFU while the other tile loads / reduces / synchronises.
+      if (a.skew_cycles != 0 && (t == 1 || j > 0)) mbar_wait(bar_x(t), (t == 1 ? j : j - 1) & 1);
+      if (trace) tr[3] = clock64();
+      float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+      uint32_t u[16];
+      exp_pack_chunk<E>(s0, u, acc0, acc1);
       tmem_st16(tP, u);
-      exp_chunk<E>(s1, u, c2v, nmc, acc0, acc1);
-      if (a.skew_cycles != 0) {  // exponentials issued: hand the MUFU to the other tile
+      if (a.skew_cycles != 0) {  // hand the MUFU over one chunk early: the other tile's wake-up overlaps our last 32 columns
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_x(t ^ 1));
       }
+      exp_pack_chunk<E>(s1, u, acc0, acc1);
       tmem_st16(tP + 16, u);
       if (trace) tr[4] = clock64();
       tc_wait_st();

@@ -59,3 +59,26 @@ __device__ __forceinline__ void mask_chunk(uint32_t (&s)[32], int col0, int vc) 
     if (col0 + i >= vc) s[i] = 0xff800000u;  // -inf
 }
 
+
+// The same in two steps, so the FMA-pipe half (scale and shift, in place) can run before a softmax warp takes its turn on
+// the MUFU and only the exponentials themselves sit inside the turn.
+__device__ __forceinline__ void scale_chunk(uint32_t (&s)[32], float2 c2, float2 nmc) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    const float2 x = ffma2(make_float2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), c2, nmc);
+    s[i] = __float_as_uint(x.x);
+    s[i + 1] = __float_as_uint(x.y);
+  }
+}
+template <typename E>
+__device__ __forceinline__ void exp_pack_chunk(const uint32_t (&s)[32], uint32_t (&u)[16], float2& acc0, float2& acc1) {
+#pragma unroll
+  for (int i = 0; i < 16; i += 2) {
+    float2 x0 = make_float2(ief_exp2(__uint_as_float(s[2 * i])), ief_exp2(__uint_as_float(s[2 * i + 1])));
+    float2 x1 = make_float2(ief_exp2(__uint_as_float(s[2 * i + 2])), ief_exp2(__uint_as_float(s[2 * i + 3])));
+    acc0 = fadd2(acc0, x0);
+    acc1 = fadd2(acc1, x1);
+    u[i] = E::pack(x0.x, x0.y);
+    u[i + 1] = E::pack(x1.x, x1.y);
+  }
+}

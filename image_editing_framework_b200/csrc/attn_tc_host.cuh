@@ -17,7 +17,7 @@ struct TcArgs {
   float scale_log2;
   int32_t perm_q[3], perm_k[3], perm_v[3];  // which of (token, head, row) feeds TMA coordinate 1..3
   IefRowTable rows;
-  int32_t skew_cycles;  // one-time start delay of query tile B's softmax warps (keeps the two tiles' exp phases out of step)
+  int32_t skew_cycles;  // experimental (attn_tc3.cu only): != 0 enables the ordered exp sections; env IEF_TC_SKEW
   long long* dbg;  // optional clock64 trace of CTA (0,0,0), see ief_debug_set_trace_buffer
 };
 
