@@ -241,6 +241,38 @@ def gen_pnp():
                          layer_outputs=rec.records, latents_per_step=per_step, latent_hw=LAT))
 
 
+XL_TINY = dict(sample_size=8, block_out_channels=(32, 64, 64), transformer_layers=(0, 2, 3), num_heads=(2, 2, 2), cross_attention_dim=32,
+               norm_num_groups=8, use_linear_projection=True, name="tiny_xl")
+
+
+def gen_pnp_xl():
+    """SDXL topology (3 blocks, several transformer layers per attention, linear projections): the *_xl hook variants."""
+    ref = load_reference("pnp")
+    pipe = make_pipeline(UNetConfig(**XL_TINY), seed=5)
+    steps, keep = 4, (0, 3)
+    prompts = ["a photo of a wooden horse", "a photo of a bronze horse"]
+    pipe.scheduler.set_timesteps(steps)
+    ts = pipe.scheduler.timesteps
+    ref.register.register_attention_control_efficient_xl(pipe, ts[:int(steps * 0.5)])
+    ref.register.register_conv_control_efficient_xl(pipe, ts[:int(steps * 0.8)])
+    rec = Recorder(pipe.unet, keep)
+    context = _context(pipe, prompts)
+    init = _latent(7, (1, 4, LAT, LAT))
+    latents = torch.cat([init, init])
+    per_step = []
+    with torch.no_grad():
+        for i, t in enumerate(ts):
+            rec.step = i
+            ref.register.register_time_xl(pipe, t.item())
+            noise = pipe.unet(torch.cat([latents] * 2), t, encoder_hidden_states=context).sample
+            nu, nc = noise.chunk(2)
+            latents = pipe.scheduler.step(nu + 7.5 * (nc - nu), t, latents).prev_sample
+            per_step.append(latents.clone())
+    n_attn = sum(1 for m in pipe.unet.modules() if type(m).__name__ == "Attention")
+    _save("pnp_xl.pt", dict(prompts=prompts, steps=steps, keep=keep, latent_seed=7, pipe_seed=5, guidance=7.5, pnp_attn_t=0.5, pnp_f_t=0.8,
+                            config=XL_TINY, layer_outputs=rec.records, latents_per_step=per_step, latent_hw=LAT, n_attention=n_attn))
+
+
 def gen_pix2pix_zero():
     ref = load_reference("pix2pix-zero")
     pipe = make_pipeline(tiny_config(), seed=4)
@@ -339,6 +371,6 @@ def gen_ddim():
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["aligner", "oracle_pins", "ddim", "p2p", "masactrl", "pnp", "pix2pix_zero", "p2p_localblend"]
+    which = sys.argv[1:] or ["aligner", "oracle_pins", "ddim", "p2p", "masactrl", "pnp", "pnp_xl", "pix2pix_zero", "p2p_localblend"]
     for w in which:
         globals()["gen_" + w]()

@@ -97,13 +97,17 @@ def run_masactrl(g, device):
     return ctrl, rec.records, per_step
 
 
-def run_pnp(g, device):
-    pipe = make_pipeline(tiny_config(), seed=g["pipe_seed"], device=device)
+def run_pnp(g, device, xl=False):
+    pipe = make_pipeline(UNetConfig(**g["config"]) if xl else tiny_config(), seed=g["pipe_seed"], device=device)
     steps = g["steps"]
     pipe.scheduler.set_timesteps(steps)
     ts = pipe.scheduler.timesteps
-    pnp.register_attention_control_efficient(pipe, ts[:int(steps * g["pnp_attn_t"])])
-    pnp.register_conv_control_efficient(pipe, ts[:int(steps * g["pnp_f_t"])])
+    if xl:
+        pnp.register_attention_control_efficient_xl(pipe, ts[:int(steps * g["pnp_attn_t"])])
+        pnp.register_conv_control_efficient_xl(pipe, ts[:int(steps * g["pnp_f_t"])])
+    else:
+        pnp.register_attention_control_efficient(pipe, ts[:int(steps * g["pnp_attn_t"])])
+        pnp.register_conv_control_efficient(pipe, ts[:int(steps * g["pnp_f_t"])])
     rec = Recorder(pipe.unet, g["keep"])
     context = editing.encode_prompts(pipe, g["prompts"])
     hw = g["latent_hw"]
@@ -114,7 +118,7 @@ def run_pnp(g, device):
     with torch.no_grad():
         for i, t in enumerate(ts.tolist()):
             rec.step = i
-            pnp.register_time(pipe, t)
+            (pnp.register_time_xl if xl else pnp.register_time)(pipe, t)
             noise = pipe.unet(torch.cat([latents] * 2), t, encoder_hidden_states=context).sample
             latents = fused.step(noise, t, latents, g["guidance"])
             per_step.append(latents.float().cpu())

@@ -63,6 +63,12 @@ def test_pnp_edit_matches_reference(cuda):
     _compare(records, per_step, g)
 
 
+def test_pnp_xl_edit_matches_reference(cuda):
+    g = golden("pnp_xl.pt")
+    records, per_step = scenarios.run_pnp(g, cuda, xl=True)
+    _compare(records, per_step, g)
+
+
 def test_pix2pix_zero_processor_matches_reference(cuda):
     g = golden("pix2pix_zero.pt")
     out, records, probs, _ = scenarios.run_pix2pix_zero(g, cuda)

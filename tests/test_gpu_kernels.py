@@ -278,3 +278,40 @@ def test_local_blend(cuda):
     assert mism < 1e-3, f"mask mismatch fraction {mism}"
     if mism == 0:
         assert torch.equal(got.cpu(), want)
+
+
+# ---------------------------------------------------------------------------------------------------- full-size properties
+# At BASELINE.json's full geometries the CPU oracle would need tens of GB of probabilities; parity is checked there through
+# size-independent properties of softmax attention (SD-2.1 @768^2: N=9216 d=64 H=5; SDXL @1024^2: N=4096 d=64 H=10; SD-1.5).
+FULL = [("sd21_96", 4, 5, 9216, 64), ("sdxl_64", 4, 10, 4096, 64), ("sd15_64", 4, 8, 4096, 40)]
+
+
+@pytest.mark.parametrize("name,B,H,N,d", FULL)
+def test_full_size_properties(cuda, name, B, H, N, d):
+    g = torch.Generator().manual_seed(N + d)
+    q, k, v = (torch.randn(B, N, H * d, generator=g).to(torch.bfloat16).to(cuda) for _ in range(3))
+    scale = d ** -0.5
+    src = [0, 0, 2, 2]
+    out = ops.attention(q, k, v, H, scale, k_src=src, v_src=src)
+    # (1) rows of softmax sum to one: with V = 1 the output is exactly representable and must be 1
+    ones = torch.ones_like(v)
+    o1 = ops.attention(q, k, ones, H, scale, k_src=src, v_src=src).float()
+    assert (o1 - 1).abs().max().item() < 1e-2
+    # (2) permuting the keys (and values alike) leaves the output unchanged
+    perm = torch.randperm(N, generator=g).to(cuda)
+    o2 = ops.attention(q, k[:, perm].contiguous(), v[:, perm].contiguous(), H, scale, k_src=src, v_src=src)
+    assert (o2.float() - out.float()).abs().max().item() < TOL
+    # (3) linear in V
+    v2 = torch.randn(B, N, H * d, generator=g).to(torch.bfloat16).to(cuda)
+    o3 = ops.attention(q, k, (v.float() + v2.float()).to(torch.bfloat16), H, scale, k_src=src, v_src=src).float()
+    o4 = ops.attention(q, k, v2, H, scale, k_src=src, v_src=src).float()
+    assert (o3 - (out.float() + o4)).abs().max().item() < 2 * TOL
+    # (4) the source-row indirection equals physically gathering the rows (MasaCtrl rows 1,3 read K,V of rows 0,2)
+    o5 = ops.attention(q, k[src].contiguous(), v[src].contiguous(), H, scale)
+    assert torch.equal(o5, out)
+    # (5) both kernel families agree, and a strip of query rows matches the fp32 oracle
+    o6 = ops.attention(q, k, v, H, scale, k_src=src, v_src=src, impl=ops.IEF_IMPL_MMA)
+    assert (o6.float() - out.float()).abs().max().item() < TOL
+    rows = slice(N - 130, N)
+    want = orc.indexed_attention(q[:, rows].cpu(), k.cpu(), v.cpu(), H, scale, k_src=src, v_src=src)
+    assert (out[:, rows].float().cpu() - want).abs().max().item() < TOL

@@ -274,6 +274,26 @@ def test_pnp_host_logic_reproduces_reference(monkeypatch):
     _compare(records, per_step, g)
 
 
+def test_pnp_xl_host_logic_reproduces_reference(monkeypatch):
+    """SDXL topology: 3 blocks, 2-3 transformer layers per attention module, linear projections; the *_xl hook tables."""
+    cpu_backend.install(monkeypatch)
+    g = golden("pnp_xl.pt")
+    records, per_step = scenarios.run_pnp(g, torch.device("cpu"), xl=True)
+    assert g["n_attention"] == 2 * (2 * 2 + 2 * 3 + 3 + 3 * 3 + 3 * 2)
+    _compare(records, per_step, g)
+    # the un-hook functions restore the original forwards
+    from image_editing_framework_b200 import pnp
+    from image_editing_framework_b200.standin.unet import UNetConfig
+    pipe = make_pipeline(UNetConfig(**g["config"]), seed=0)
+    before = [m.forward for m in pipe.unet.modules() if type(m).__name__ == "Attention"]
+    pnp.register_attention_control_efficient_xl(pipe, [1])
+    pnp.register_conv_control_efficient_xl(pipe, [1])
+    pnp.unregister_attention_control_efficient_xl(pipe)
+    pnp.unregister_conv_control_efficient_xl(pipe)
+    after = [m.forward for m in pipe.unet.modules() if type(m).__name__ == "Attention"]
+    assert all(a == b for a, b in zip(before, after))
+
+
 def test_pix2pix_zero_processor_reproduces_reference(monkeypatch):
     cpu_backend.install(monkeypatch)
     g = golden("pix2pix_zero.pt")
