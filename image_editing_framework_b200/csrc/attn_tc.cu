@@ -363,23 +363,20 @@ int ief_attn_tc_launch(const ief_attn_params* p, const IefRowTable& rows, cudaSt
   a.scale_log2 = p->scale * kLog2e;
   a.rows = rows;
   a.dbg = ief_debug_trace_buffer();
-  static int skew = -1;
-  if (skew < 0) { const char* e = getenv("IEF_TC_SKEW"); skew = e ? atoi(e) : 1; }
-  a.skew_cycles = skew;
   CUtensorMap mq, mk, mv;
   int rc;
   if ((rc = make_map(&mq, p->dtype, p->q, p->d, p->Nq, p->H, p->B, a.perm_q)) != IEF_OK) return rc;
   if ((rc = make_map(&mk, p->dtype, p->k, p->d, p->Nk, p->H, p->B, a.perm_k)) != IEF_OK) return rc;
   if ((rc = make_map(&mv, p->dtype, p->v, p->d, p->Nk, p->H, p->B, a.perm_v)) != IEF_OK) return rc;
   // Kernel generations (IEF_TC_VERSION=1|2|3 caps the generation for A/B measurements):
-  //   head_dim <= 64 : 128-row split-KV CTAs (attn_tc2s) when that shortens the estimated wave time, else the third generation
-  //                    (attn_tc3: 256-row CTAs, column-split softmax, ordered exp sections)
+  //   head_dim <= 64 : third generation (attn_tc3: column-split softmax, ordered exp sections), as 128-row split-KV CTAs when
+  //                    that shortens the estimated wave time, else as 256-row CTAs; generation 2: attn_tc2s / attn_tc2
   //   head_dim <= 128: second generation (attn_tc2, P aliased onto S)        above: first generation (this file)
   static int version = -1;
   if (version < 0) { const char* e = getenv("IEF_TC_VERSION"); version = (e && e[0] >= '1' && e[0] <= '3') ? e[0] - '0' : 3; }
   if (version >= 2 && dch == 1) {
     // 256-row CTAs (two query tiles share K/V) or 128-row CTAs (two key halves share Q)? Estimated time = waves x (key steps
-    // per CTA + fixed prologue/epilogue, about three steps' worth): take the smaller. IEF_TC_SPLITKV=0|1 forces the choice.
+    // per CTA + fixed prologue/epilogue, about three steps' worth): take the smaller. IEF_TC_SPLITKV=0|1|2 forces pair / split / hybrid.
     static int force = -2, sms = 0;
     if (force == -2) {
       const char* e = getenv("IEF_TC_SPLITKV");
@@ -389,14 +386,19 @@ int ief_attn_tc_launch(const ief_attn_params* p, const IefRowTable& rows, cudaSt
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
       if (sms <= 0) sms = 148;
     }
-    int active = 0;
-    for (int i = 0; i < p->B; ++i) active += rows.active[i] ? 1 : 0;
+    // estimated time in units of one key step: waves x (steps per CTA + ~3 steps of prologue/epilogue)
     const int nt = a.nt1 + a.nt2;
-    const long n_pair = (long)ief_ceil_div(p->Nq, 2 * kBM) * p->H * active, n_split = (long)ief_ceil_div(p->Nq, kBM) * p->H * active;
-    const long t_pair = ((n_pair + sms - 1) / sms) * (nt + 3), t_split = ((n_split + sms - 1) / sms) * ((nt + 1) / 2 + 3);
-    const bool split = force >= 0 ? force != 0 : t_split < t_pair;
-    if (split) return ief_attn_tc2s_launch(p, mq, mk, mv, a, st);
-    if (version >= 3) return ief_attn_tc3_launch(p, mq, mk, mv, a, st);
+    const long pairs = (long)ief_ceil_div(p->Nq, 2 * kBM) * p->H * p->B;
+    const long full = pairs / sms, rest = pairs % sms;
+    const long t_pair = (full + (rest ? 1 : 0)) * (nt + 3);
+    const long t_split = ((2 * pairs + sms - 1) / sms) * ((nt + 1) / 2 + 3);
+    const long t_hybrid = full * (nt + 3) + ((2 * rest + sms - 1) / sms) * ((nt + 1) / 2 + 3) + (rest ? 1 : 0);  // +1: second launch
+    int mode = 0;  // 0 pair, 1 split, 2 hybrid
+    if (force >= 0) mode = force;
+    else if (t_hybrid < t_pair && t_hybrid <= t_split && full > 0 && rest > 0) mode = 2;
+    else if (t_split < t_pair) mode = 1;
+    if (version >= 3) return ief_attn_tc3_launch(p, mq, mk, mv, a, mode, st);
+    if (mode == 1) return ief_attn_tc2s_launch(p, mq, mk, mv, a, st);
   }
   if (version >= 2 && dch <= 2) return ief_attn_tc2_launch(p, mq, mk, mv, a, st);
   dim3 grid(ief_ceil_div(p->Nq, kBM), p->H, p->B);

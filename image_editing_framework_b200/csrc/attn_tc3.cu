@@ -1,20 +1,25 @@
-// Controlled self-attention for sm_100a, third generation (head_dim <= 64): the second-generation schedule (attn_tc2.cu,
-// two 128-row query tiles ping-ponging through a split S | P | O TMEM layout) with each tile's softmax spread over TWO
-// warpgroups that own the left / right 64 score columns of every row.
+// Controlled self-attention for sm_100a, third generation (head_dim <= 64).
 //
 //   O[b] = softmax(scale * Q[q_src[b]] K[k_src[b]]^T) V[v_src[b]]        (ief_attn_fwd, include/ief_b200.h)
 //
-// Why: the exp pipe (MUFU, 8 cycles per warp instruction per SM sub-partition) is the binding unit at head_dim 40-64.
-// Measured (tools/micro/mufu.cu): one softmax warp per sub-partition keeps it 84 % busy, two keep it 98 % busy. With one
-// warpgroup per tile only one warp per sub-partition is in its exp phase most of the time; with two, whichever tile is
-// in its exp phase saturates the pipe on its own while the other tile loads / reduces / synchronises.
+// One CTA per SM keeps TWO independent online-softmax streams (t = 0,1) in flight over a split TMEM layout
+//   S_0 0 | S_1 128 | P_0 256 | P_1 320 | O_0 384 | O_1 448      (512 columns)
+// so that QK(j+1) of a stream is issued as soon as its S(j) sits in the softmax registers. Two flavours, one template:
+//   SPLIT = false  the streams are two 128-row QUERY tiles sharing the K/V ring           (256-row CTAs)
+//   SPLIT = true   the streams are the two halves of the KEY range of ONE query tile, sharing Q; their partial (O, max, sum)
+//                  are merged through shared memory at the end                            (128-row CTAs: twice as many,
+//                  half as long — the cure for wave quantisation, e.g. SD-1.5's 64x64 layer: 3.46 -> 6.92 waves)
 //
-//   warp 0        TMA producer            warp 1   tcgen05.mma issuer       warps 2,3  idle (register donors)
-//   warps 4-11    tile A: columns 0-63 (warps 4-7) and 64-127 (warps 8-11) of every score row
-//   warps 12-19   tile B likewise
-// The two halves of a row exchange their partial row maximum through shared memory (one 256-thread named barrier per
-// key tile) so both scale with the same reference; partial row sums are merged once in the epilogue. Each half rescales
-// and writes back its share of the O columns.
+// Why 20 warps: the exp pipe (MUFU, 8 cycles per warp instruction per SM sub-partition) is the binding unit at head_dim
+// 40-64 and one softmax warp per sub-partition only keeps it 84 % busy (two: 98 %, tools/micro/mufu.cu). Each stream's
+// softmax is therefore spread over TWO warpgroups owning the left / right 64 score columns of every row:
+//   warp 0   TMA producer      warp 1   tcgen05.mma issuer (elected lane)      warps 2,3   idle register donors (setmaxnreg)
+//   warps 4-11   stream 0: columns 0-63 (warps 4-7) and 64-127 (warps 8-11)      warps 12-19   stream 1 likewise
+// The halves of a row exchange their partial row maximum through shared memory (one 256-thread named barrier per key
+// tile); partial row sums are merged in the epilogue; each half rescales / writes back its share of the O columns.
+// The two streams' exp sections are strictly ORDERED (the ping-pong of FlashAttention-3/4): left alone they fall into
+// lock-step and idle the MUFU together. Scale/shift (FMA pipe) happens before a stream takes its turn, and the turn is
+// handed over one 32-column chunk early so the other stream's wake-up overlaps the tail.
 #include "ief_common.cuh"
 #include "ptx_sm100.cuh"
 #include "attn_tc_host.cuh"
@@ -28,39 +33,52 @@ namespace {
 constexpr int kBM = 128, kBN = 128;
 constexpr int kThreads = 640;
 constexpr int kRegsLow = 32, kRegsHigh = 112;  // pool = 640 threads x 96 regs at launch (61440): 128*32 + 512*112 = 61440
-constexpr int kStages = 3;
-constexpr int kTileBytes = kTcChunkBytes;                    // head_dim <= 64: one 64-channel chunk per tile
-constexpr int kSmemData = kTileBytes * (2 + 2 * kStages);    // Q_A Q_B | K ring | V ring
-constexpr int kSmemXchg = 6 * 1024;                          // row-max exchange [2 parities][2 tiles][2 halves][128] + row-sum [2][2][128]
-constexpr int kSmemBytes = kSmemData + kSmemXchg + 1024 + 256;
+constexpr int ST = 3;
+constexpr int kTile = kTcChunkBytes;           // 16 KiB: one [128 x 64ch] box (head_dim <= 64)
+constexpr int kSmemXchg = 8 * 1024;            // floats: row-max exchange [2 parities][2 streams][2 halves][128] | row sums [2][2][128] | split merge [2][128]
 constexpr float kRescaleThreshold = 8.0f;
+
+template <bool SPLIT> struct Cfg3 {
+  static constexpr int kQTiles = SPLIT ? 1 : 2;
+  static constexpr int kRingTiles = SPLIT ? 2 : 1;                       // K (and V) tiles per ring stage
+  static constexpr int kSmemData = kTile * (kQTiles + 2 * ST * kRingTiles);
+  static constexpr int kSmemBytes = kSmemData + kSmemXchg + 1024 + 256;
+};
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
-template <int DTYPE>
+template <int DTYPE, bool SPLIT>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                 const __grid_constant__ TcArgs a) {
   using E = ElemT<DTYPE>;
-  constexpr int ST = kStages;
-  const int b = blockIdx.z, h = blockIdx.y, qt = blockIdx.x;
+  using Cfg = Cfg3<SPLIT>;
+  constexpr int RT = Cfg::kRingTiles;
+  // 1-D grid over linearised work items so that a launch can cover any contiguous range of them (hybrid pair + split launches)
+  const int lin = blockIdx.x + a.work_offset;
+  const int qt = lin % a.nq_blocks;  // 256-row block (pair) or 128-row tile (split)
+  const int h = (lin / a.nq_blocks) % a.H, b = lin / (a.nq_blocks * a.H);
   if (!a.rows.active[b]) return;
+  const bool cta_trace = a.dbg != nullptr && lin == 0;
+  if (cta_trace && threadIdx.x == 0) a.dbg[1536] = clock64();
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
-  auto sQ = [&](int t) { return base + kTileBytes * t; };
-  auto sK = [&](int s) { return base + kTileBytes * (2 + s); };
-  auto sV = [&](int s) { return base + kTileBytes * (2 + ST + s); };
-  float* xmax = reinterpret_cast<float*>(base_ptr + kSmemData);         // [parity][tile][half][128]
-  float* xsum = xmax + 2 * 2 * 2 * 128;                                 // [tile][half][128]
-  const uint32_t bar0 = base + kSmemData + kSmemXchg;
+  auto sQ = [&](int t) { return base + kTile * (SPLIT ? 0 : t); };
+  auto sK = [&](int s, int t) { return base + kTile * (Cfg::kQTiles + RT * s + (SPLIT ? t : 0)); };
+  auto sV = [&](int s, int t) { return base + kTile * (Cfg::kQTiles + RT * ST + RT * s + (SPLIT ? t : 0)); };
+  float* stage_o = reinterpret_cast<float*>(base_ptr + kTile * Cfg::kQTiles);  // split merge staging: K ring stage 0 (32 KiB), [col][row]
+  float* xmax = reinterpret_cast<float*>(base_ptr + Cfg::kSmemData);          // [parity][stream][half][128]
+  float* xsum = xmax + 2 * 2 * 2 * 128;                                       // [stream][half][128]
+  float* xml = xsum + 2 * 2 * 128;                                            // split merge: [0..127] max, [128..255] sum of stream 1
+  const uint32_t bar0 = base + Cfg::kSmemData + kSmemXchg;
   const uint32_t bar_q = bar0;
   auto bar_s = [&](int t) { return bar0 + 8 + 8 * t; };    // S_t complete in TMEM
-  auto bar_p = [&](int t) { return bar0 + 24 + 8 * t; };   // P_t written by the 256 softmax threads of tile t
-  auto bar_c = [&](int t) { return bar0 + 40 + 8 * t; };   // S_t in registers of its 8 softmax warps
+  auto bar_p = [&](int t) { return bar0 + 24 + 8 * t; };   // P_t written by the 256 softmax threads of stream t
+  auto bar_c = [&](int t) { return bar0 + 40 + 8 * t; };   // S_t in the registers of its 8 softmax warps
   auto bar_o = [&](int t) { return bar0 + 56 + 8 * t; };   // PV_t(j) complete
-  auto bar_x = [&](int t) { return bar0 + 72 + 8 * t; };   // exp turn of tile t (granted by the 8 warps of the other tile)
+  auto bar_x = [&](int t) { return bar0 + 72 + 8 * t; };   // exp turn of stream t (granted by the 8 warps of the other stream)
   auto bar_kf = [&](int s) { return bar0 + 88 + 8 * s; };
   auto bar_ke = [&](int s) { return bar0 + 88 + 8 * (ST + s); };
   auto bar_vf = [&](int s) { return bar0 + 88 + 8 * (2 * ST + s); };
@@ -70,6 +88,16 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nt = a.nt1 + a.nt2;
+  // key tiles per stream: pair -> both streams see all nt tiles; split -> [0, nt0) and [nt0, nt)
+  const int nt0 = SPLIT ? (nt + 1) >> 1 : nt, nt1 = SPLIT ? nt - nt0 : nt;
+  auto stream_nt = [&](int t) { return t == 0 ? nt0 : nt1; };
+  auto global_tile = [&](int t, int j) { return SPLIT && t == 1 ? nt0 + j : j; };
+  auto kv_coord = [&](int g, int& jj, int& kb, int& vb) {  // global key tile -> (tile inside its key block, source rows)
+    const bool blk2 = g >= a.nt1;
+    jj = blk2 ? g - a.nt1 : g;
+    kb = blk2 ? a.rows.k2[b] : a.rows.k[b];
+    vb = blk2 ? a.rows.v2[b] : a.rows.v[b];
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -99,34 +127,38 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
-  // TMEM columns: S_A 0 | S_B 128 | P_A 256 | P_B 320 | O_A 384 | O_B 448
+  if (cta_trace && threadIdx.x == 0) a.dbg[1537] = clock64();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     reg_dec<kRegsLow>();
     const int qb = a.rows.q[b];
     if (elect_one()) {
-      mbar_arrive_expect_tx(bar_q, 2 * kTileBytes);
-      tc_tma_tile(sQ(0), &tmQ, bar_q, 0, (2 * qt) * kBM, h, qb, a.perm_q);
-      tc_tma_tile(sQ(1), &tmQ, bar_q, 0, (2 * qt + 1) * kBM, h, qb, a.perm_q);
+      mbar_arrive_expect_tx(bar_q, Cfg::kQTiles * kTile);
+      for (int t = 0; t < Cfg::kQTiles; ++t) tc_tma_tile(sQ(t), &tmQ, bar_q, 0, (Cfg::kQTiles * qt + t) * kBM, h, qb, a.perm_q);
     }
     __syncwarp();
-    for (int j = 0; j < nt; ++j) {
+    for (int j = 0; j < nt0; ++j) {
       const int s = j % ST, ph = (j / ST) & 1;
-      const bool blk2 = j >= a.nt1;
-      const int jj = blk2 ? j - a.nt1 : j;
-      const int kb = blk2 ? a.rows.k2[b] : a.rows.k[b];
-      const int vb = blk2 ? a.rows.v2[b] : a.rows.v[b];
+      const int nload = SPLIT ? (j < nt1 ? 2 : 1) : 1;
       mbar_wait(bar_ke(s), ph ^ 1);
       if (elect_one()) {
-        mbar_arrive_expect_tx(bar_kf(s), kTileBytes);
-        tc_tma_tile(sK(s), &tmK, bar_kf(s), 0, jj * kBN, h, kb, a.perm_k);
+        mbar_arrive_expect_tx(bar_kf(s), nload * kTile);
+        for (int t = 0; t < nload; ++t) {
+          int jj, kb, vb;
+          kv_coord(global_tile(t, j), jj, kb, vb);
+          tc_tma_tile(sK(s, t), &tmK, bar_kf(s), 0, jj * kBN, h, kb, a.perm_k);
+        }
       }
       __syncwarp();
       mbar_wait(bar_ve(s), ph ^ 1);
       if (elect_one()) {
-        mbar_arrive_expect_tx(bar_vf(s), kTileBytes);
-        tc_tma_tile(sV(s), &tmV, bar_vf(s), 0, jj * kBN, h, vb, a.perm_v);
+        mbar_arrive_expect_tx(bar_vf(s), nload * kTile);
+        for (int t = 0; t < nload; ++t) {
+          int jj, kb, vb;
+          kv_coord(global_tile(t, j), jj, kb, vb);
+          tc_tma_tile(sV(s, t), &tmV, bar_vf(s), 0, jj * kBN, h, vb, a.perm_v);
+        }
       }
       __syncwarp();
     }
@@ -137,56 +169,60 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint64_t desc_v = make_smem_desc_sw128(0, kTcChunkBytes, 1024);
     auto issue_qk = [&](int t, int s) {
       for (int k = 0; k < a.ksteps_qk; ++k)
-        umma_ss(tmem_base + 128 * t, desc_k | ((sQ(t) + k * 32) >> 4), desc_k | ((sK(s) + k * 32) >> 4), a.idesc_qk, k > 0);
+        umma_ss(tmem_base + 128 * t, desc_k | ((sQ(t) + k * 32) >> 4), desc_k | ((sK(s, t) + k * 32) >> 4), a.idesc_qk, k > 0);
       umma_commit(bar_s(t));
     };
     auto issue_pv = [&](int t, int s, bool acc) {
 #pragma unroll
       for (int k = 0; k < kBN / 16; ++k)
-        umma_ts(tmem_base + 384 + 64 * t, tmem_base + 256 + 64 * t + k * 8, desc_v | ((sV(s) + k * 2048) >> 4), a.idesc_pv, acc || (k > 0));
+        umma_ts(tmem_base + 384 + 64 * t, tmem_base + 256 + 64 * t + k * 8, desc_v | ((sV(s, t) + k * 2048) >> 4), a.idesc_pv, acc || (k > 0));
     };
     mbar_wait(bar_q, 0);
     mbar_wait(bar_kf(0), 0);
     tc_fence_after();
     if (elect_one()) {
       issue_qk(0, 0);
-      issue_qk(1, 0);
+      if (nt1 > 0) issue_qk(1, 0);
       umma_commit(bar_ke(0));
     }
     __syncwarp();
-    for (int j = 0; j < nt; ++j) {
+    for (int j = 0; j < nt0; ++j) {
       const int s = j % ST, ph = (j / ST) & 1;
       const int s1 = (j + 1) % ST, ph1 = ((j + 1) / ST) & 1;
-      if (j + 1 < nt) {  // next score tiles first: they only need S_t(j) to be in the softmax registers
+      if (j + 1 < nt0) {  // next score tiles first: they only need S_t(j) to be in the softmax registers
         mbar_wait(bar_kf(s1), ph1);
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
-          mbar_wait(bar_c(t), j & 1);
-          tc_fence_after();
-          if (elect_one()) {
-            issue_qk(t, s1);
-            if (t == 1) umma_commit(bar_ke(s1));
+          if (j + 1 < stream_nt(t)) {
+            mbar_wait(bar_c(t), j & 1);
+            tc_fence_after();
+            if (elect_one()) issue_qk(t, s1);
+            __syncwarp();
           }
-          __syncwarp();
         }
+        if (elect_one()) umma_commit(bar_ke(s1));
+        __syncwarp();
       }
       mbar_wait(bar_vf(s), ph);
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
-        mbar_wait(bar_p(t), j & 1);
-        tc_fence_after();
-        if (elect_one()) {
-          issue_pv(t, s, j > 0);
-          umma_commit(bar_o(t));
-          if (t == 1) umma_commit(bar_ve(s));
+        if (j < stream_nt(t)) {
+          mbar_wait(bar_p(t), j & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            issue_pv(t, s, j > 0);
+            umma_commit(bar_o(t));
+          }
+          __syncwarp();
         }
-        __syncwarp();
       }
+      if (elect_one()) umma_commit(bar_ve(s));
+      __syncwarp();
     }
   } else if (warp < 4) {
     reg_dec<kRegsLow>();
   } else {
-    // ------------------------------------------------------------------ softmax of tile t, column half `half`
+    // ------------------------------------------------------------------ softmax of stream t, column half `half`
     reg_inc<kRegsHigh>();
     const int idx = warp - 4;
     const int t = idx >> 3, half = (idx >> 2) & 1;
@@ -199,11 +235,16 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const float c2 = a.scale_log2;
     float m_used = -INFINITY, l = 0.f;
     const int nchunk_o = a.dv_mma >> 4;
-    for (int j = 0; j < nt; ++j) {
-      const bool blk2 = j >= a.nt1;
-      const int jj = blk2 ? j - a.nt1 : j;
+    const int my_nt = stream_nt(t);
+
+    // Turn protocol: exp sections alternate 0(0) 1(0) 0(1) 1(1) ...; stream 0 waits for stream 1's previous section, stream
+    // 1 for stream 0's current one. In the split flavour stream 1 may be one step short (odd tile count): stream 0's last
+    // grant then simply goes unused.
+    for (int j = 0; j < my_nt; ++j) {
+      int jj, kb_unused, vb_unused;
+      kv_coord(global_tile(t, j), jj, kb_unused, vb_unused);
       const int vc = min(kBN, a.Nk - jj * kBN);
-      const bool trace = a.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && row == 0 && half == 0 && j < 64;
+      const bool trace = a.dbg != nullptr && lin == 0 && row == 0 && half == 0 && j < 64;
       long long* tr = trace ? a.dbg + (t * 64 + j) * 8 : nullptr;
       if (trace) tr[0] = clock64();
       mbar_wait(bar_s(t), j & 1);
@@ -250,30 +291,22 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           m_used = m_new;
         }
       }
-      // Ordered exp sections (the ping-pong of FlashAttention-3/4): tile A's and tile B's exponentials strictly alternate,
-      // so each runs on an uncontended MUFU while the other tile loads / reduces / synchronises. Left to themselves the two
-      // tiles fall into lock-step (both idle the MUFU during their non-exp phases, then share it).
       const float mc = m_used * c2;
       const float2 c2v = make_float2(c2, c2), nmc = make_float2(-mc, -mc);
-      scale_chunk(s0, c2v, nmc);   // FMA pipe work, outside the MUFU turn
+      scale_chunk(s0, c2v, nmc);   // FMA-pipe work, outside the MUFU turn
       scale_chunk(s1, c2v, nmc);
       if (!o_ready) {  // PV_t(j-1) must have finished reading P_t; wait for it BEFORE taking the exp turn, not inside it
         mbar_wait(bar_o(t), (j - 1) & 1);
         tc_fence_after();
-        o_ready = true;
       }
-      // Ordered exp sections (the ping-pong of FlashAttention-3/4): tile A's and tile B's exponentials strictly alternate,
-      // so each runs on an uncontended MUFU while the other tile loads / reduces / synchronises.
-      if (a.skew_cycles != 0 && (t == 1 || j > 0)) mbar_wait(bar_x(t), (t == 1 ? j : j - 1) & 1);
+      if (t == 1 || j > 0) mbar_wait(bar_x(t), (t == 1 ? j : j - 1) & 1);   // ordered exp sections
       if (trace) tr[3] = clock64();
       float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
       uint32_t u[16];
       exp_pack_chunk<E>(s0, u, acc0, acc1);
       tmem_st16(tP, u);
-      if (a.skew_cycles != 0) {  // hand the MUFU over one chunk early: the other tile's wake-up overlaps our last 32 columns
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_x(t ^ 1));
-      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_x(t ^ 1));  // hand the MUFU over one chunk early
       exp_pack_chunk<E>(s1, u, acc0, acc1);
       tmem_st16(tP + 16, u);
       if (trace) tr[4] = clock64();
@@ -284,59 +317,119 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       acc0 = fadd2(acc0, acc1);
       l += acc0.x + acc0.y;
     }
-    // epilogue: merge the two halves' row sums, then each half writes its share of O / l
-    mbar_wait(bar_o(t), (nt - 1) & 1);
-    tc_fence_after();
+    if (cta_trace && warp == 4 && lane == 0) a.dbg[1538] = clock64();
+    if (my_nt > 0) {
+      mbar_wait(bar_o(t), (my_nt - 1) & 1);
+      tc_fence_after();
+    }
+    if (cta_trace && warp == 4 && lane == 0) a.dbg[1539] = clock64();
+    // ---- epilogue: merge the two column halves' row sums ...
     float* xs = xsum + t * 2 * 128;
     xs[half * 128 + row] = l;
     named_bar_sync(1 + t, 256);
-    const float inv = 1.f / (l + xs[(half ^ 1) * 128 + row]);
-    const int grow = (2 * qt + t) * kBM + row;
-    typename E::T* op = reinterpret_cast<typename E::T*>(a.o) + (int64_t)b * a.o_sb + (int64_t)grow * a.o_sn + (int64_t)h * a.o_sh;
+    float lrow = l + xs[(half ^ 1) * 128 + row];
     const int nchunk_d = (a.d + 15) >> 4;
-    for (int cc = half; cc < nchunk_d; cc += 2) {
-      uint32_t r[16];
-      tmem_ld16(tO + 16 * cc, r);
-      tc_wait_ld();
-      if (grow < a.Nq) {
-        uint4 v0, v1;
-        v0.x = E::pack(__uint_as_float(r[0]) * inv, __uint_as_float(r[1]) * inv);
-        v0.y = E::pack(__uint_as_float(r[2]) * inv, __uint_as_float(r[3]) * inv);
-        v0.z = E::pack(__uint_as_float(r[4]) * inv, __uint_as_float(r[5]) * inv);
-        v0.w = E::pack(__uint_as_float(r[6]) * inv, __uint_as_float(r[7]) * inv);
-        v1.x = E::pack(__uint_as_float(r[8]) * inv, __uint_as_float(r[9]) * inv);
-        v1.y = E::pack(__uint_as_float(r[10]) * inv, __uint_as_float(r[11]) * inv);
-        v1.z = E::pack(__uint_as_float(r[12]) * inv, __uint_as_float(r[13]) * inv);
-        v1.w = E::pack(__uint_as_float(r[14]) * inv, __uint_as_float(r[15]) * inv);
-        if (16 * cc + 8 <= a.d) *reinterpret_cast<uint4*>(op + 16 * cc) = v0;
-        if (16 * cc + 16 <= a.d) *reinterpret_cast<uint4*>(op + 16 * cc + 8) = v1;
+    float wmine = 1.f, wother = 0.f;
+    if constexpr (SPLIT) {
+      // ... then the two key halves. When stream 1's last PV has completed, every QK MMA of the CTA has completed too
+      // (program order of the issuing thread), so the K ring is free to serve as staging; the V ring may still be in use.
+      if (t == 1 && nt1 > 0) {
+        if (half == 0) {
+          xml[row] = m_used;
+          xml[128 + row] = lrow;
+        }
+        for (int cc = half; cc < nchunk_d; cc += 2) {
+          uint32_t r[16];
+          tmem_ld16(tO + 16 * cc, r);
+          tc_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) stage_o[(16 * cc + i) * 128 + row] = __uint_as_float(r[i]);
+        }
+      }
+      named_bar_sync(3, 512);
+      if (t == 0 && nt1 > 0) {
+        const float mB = xml[row], lB = xml[128 + row];
+        const float m = fmaxf(m_used, mB);
+        wmine = ief_exp2((m_used - m) * c2);
+        wother = ief_exp2((mB - m) * c2);
+        lrow = lrow * wmine + lB * wother;
+      }
+    }
+    if (!SPLIT || t == 0) {
+      const float inv = 1.f / lrow;
+      wmine *= inv;
+      wother *= inv;
+      const int grow = (Cfg::kQTiles * qt + (SPLIT ? 0 : t)) * kBM + row;
+      typename E::T* op = reinterpret_cast<typename E::T*>(a.o) + (int64_t)b * a.o_sb + (int64_t)grow * a.o_sn + (int64_t)h * a.o_sh;
+      for (int cc = half; cc < nchunk_d; cc += 2) {
+        uint32_t r[16];
+        tmem_ld16(tO + 16 * cc, r);
+        tc_wait_ld();
+        float f[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          f[i] = __uint_as_float(r[i]) * wmine;
+          if (SPLIT && nt1 > 0) f[i] = fmaf(stage_o[(16 * cc + i) * 128 + row], wother, f[i]);
+        }
+        if (grow < a.Nq) {
+          uint4 v0, v1;
+          v0.x = E::pack(f[0], f[1]); v0.y = E::pack(f[2], f[3]); v0.z = E::pack(f[4], f[5]); v0.w = E::pack(f[6], f[7]);
+          v1.x = E::pack(f[8], f[9]); v1.y = E::pack(f[10], f[11]); v1.z = E::pack(f[12], f[13]); v1.w = E::pack(f[14], f[15]);
+          if (16 * cc + 8 <= a.d) *reinterpret_cast<uint4*>(op + 16 * cc) = v0;
+          if (16 * cc + 16 <= a.d) *reinterpret_cast<uint4*>(op + 16 * cc + 8) = v1;
+        }
       }
     }
   }
+  if (cta_trace && warp == 4 && lane == 0) a.dbg[1540] = clock64();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+  if (cta_trace && threadIdx.x == 32) a.dbg[1541] = clock64();
 }
 
-template <int DTYPE>
-int launch_tc3(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const TcArgs& a, dim3 grid, cudaStream_t st) {
-  auto kern = attn_tc3_kernel<DTYPE>;
+template <int DTYPE, bool SPLIT>
+int launch_tc3(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, TcArgs a, int first, int count, int nq_blocks, cudaStream_t st) {
+  auto kern = attn_tc3_kernel<DTYPE, SPLIT>;
   static bool configured = false;
   if (!configured) {
-    IEF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    IEF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg3<SPLIT>::kSmemBytes));
     configured = true;
   }
-  kern<<<grid, kThreads, kSmemBytes, st>>>(mq, mk, mv, a);
+  if (count <= 0) return IEF_OK;
+  a.work_offset = first;
+  a.nq_blocks = nq_blocks;
+  kern<<<count, kThreads, Cfg3<SPLIT>::kSmemBytes, st>>>(mq, mk, mv, a);
   IEF_LAUNCH_OK("attn_tc3_kernel");
   return IEF_OK;
 }
 
+template <int DTYPE>
+int launch_mode(const ief_attn_params* p, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const TcArgs& a, int mode, cudaStream_t st) {
+  const int nqp = ief_ceil_div(p->Nq, 2 * kBM);         // 256-row blocks per (row, head)
+  const int pairs = nqp * p->H * p->B;
+  if (mode == 0) return launch_tc3<DTYPE, false>(mq, mk, mv, a, 0, pairs, nqp, st);
+  if (mode == 1) return launch_tc3<DTYPE, true>(mq, mk, mv, a, 0, 2 * pairs, 2 * nqp, st);
+  // hybrid: the full waves as 256-row CTAs, the remaining r < #SM/2 pairs as 2r half-length split-KV CTAs (pair L = split 2L, 2L+1)
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  const int full = (pairs / sms) * sms, rest = pairs - full;
+  int rc = launch_tc3<DTYPE, false>(mq, mk, mv, a, 0, full, nqp, st);
+  if (rc != IEF_OK) return rc;
+  return launch_tc3<DTYPE, true>(mq, mk, mv, a, 2 * full, 2 * rest, 2 * nqp, st);
+}
+
 }  // namespace
 
-int ief_attn_tc3_launch(const ief_attn_params* p, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const TcArgs& a, cudaStream_t st) {
-  dim3 grid(ief_ceil_div(p->Nq, 2 * kBM), p->H, p->B);
-  return p->dtype == IEF_BF16 ? launch_tc3<IEF_BF16>(mq, mk, mv, a, grid, st) : launch_tc3<IEF_F16>(mq, mk, mv, a, grid, st);
+int ief_attn_tc3_launch(const ief_attn_params* p, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const TcArgs& a, int mode,
+                        cudaStream_t st) {
+  return p->dtype == IEF_BF16 ? launch_mode<IEF_BF16>(p, mq, mk, mv, a, mode, st) : launch_mode<IEF_F16>(p, mq, mk, mv, a, mode, st);
 }

@@ -16,8 +16,9 @@ struct TcArgs {
   uint32_t idesc_qk, idesc_pv;
   float scale_log2;
   int32_t perm_q[3], perm_k[3], perm_v[3];  // which of (token, head, row) feeds TMA coordinate 1..3
+  int32_t work_offset;  // attn_tc3: first linear work item (q block + nq_blocks * (head + H * row)) of this launch
+  int32_t nq_blocks;    // attn_tc3: query blocks per (row, head) in this launch's flavour
   IefRowTable rows;
-  int32_t skew_cycles;  // experimental (attn_tc3.cu only): != 0 enables the ordered exp sections; env IEF_TC_SKEW
   long long* dbg;  // optional clock64 trace of CTA (0,0,0), see ief_debug_set_trace_buffer
 };
 
@@ -28,6 +29,7 @@ __device__ __forceinline__ void tc_tma_tile(uint32_t dst, const CUtensorMap* m, 
 }
 
 long long* ief_debug_trace_buffer();
-int ief_attn_tc3_launch(const ief_attn_params* p, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const TcArgs& a, cudaStream_t st);
+int ief_attn_tc3_launch(const ief_attn_params* p, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const TcArgs& a, int mode,
+                        cudaStream_t st);  // mode: 0 pair, 1 split, 2 hybrid (full waves as pairs, remainder split)
 int ief_attn_tc2s_launch(const ief_attn_params* p, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const TcArgs& a, cudaStream_t st);
 int ief_attn_tc2_launch(const ief_attn_params* p, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const TcArgs& a, cudaStream_t st);

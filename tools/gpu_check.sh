@@ -7,9 +7,11 @@ run() { name=$1; shift; echo "=== $name" ; timeout 600 python -m pytest tests/te
 run probe "umma_probe"
 run mma "attn_mma or probs_out or rejects"
 run tc "tcgen05 or fp16 or row_sources or masactrl or lazy or auto or strided"
-IEF_TC_VERSION=2 IEF_TC_SPLITKV=0 run tc_v2 "tcgen05 or fp16 or row_sources or masactrl or lazy or strided"
-IEF_TC_SPLITKV=1 run tc_splitkv "tcgen05 or fp16 or row_sources or masactrl or lazy or strided"
+IEF_TC_VERSION=2 IEF_TC_SPLITKV=0 run tc_v2_pair "tcgen05 or fp16 or row_sources or masactrl or lazy or strided"
+IEF_TC_SPLITKV=1 run tc_v3_split "tcgen05 or fp16 or row_sources or masactrl or lazy or strided"
+IEF_TC_SPLITKV=2 run tc_v3_hybrid "tcgen05 or fp16 or row_sources or masactrl or lazy or strided"
 IEF_TC_SPLITKV=0 run tc_v3_pair "tcgen05 or fp16 or row_sources or masactrl or lazy or strided"
+IEF_TC_VERSION=2 IEF_TC_SPLITKV=1 run tc_v2_split "tcgen05 or fp16 or row_sources or masactrl or lazy or strided"
 IEF_TC_VERSION=1 run tc_v1 "tcgen05 or fp16 or row_sources or masactrl or lazy or strided"
 run cross "cross_attention"
 run elem "ddim or accumulate or local_blend"

@@ -36,5 +36,11 @@ for tt in range(2):
     for j in range(2, min(nt - 1, 14)):
         r = mm[tt, j]
         print(f"t{tt} j={j:2d} at={int(r[0]) - t0:7d} wait_P={int(r[1] - r[0]):5d} issue={int(r[3] - r[1]):4d}")
+c = t[1536:1542]
+if int(c[0]) != 0:
+    k0 = int(c[0])
+    print(f"CTA phases (cycles from kernel entry): setup done={int(c[1]) - k0}  first S wait start={t0 - k0}  first S ready={int(sm[0, 0, 1]) - k0}  "
+          f"loop end={int(c[2]) - k0}  last PV done={int(c[3]) - k0}  epilogue done={int(c[4]) - k0}  CTA exit={int(c[5]) - k0}")
+    print("first steps wg0:", [(int(sm[0, j, 0]) - k0, int(sm[0, j, 5]) - k0) for j in range(0, 3)])
 tot = int(sm[0, nt - 1, 5] - sm[0, 0, 0])
 print(f"total cycles for {nt} tiles (wg0): {tot}  -> {tot / nt:.0f} per tile-pair")
