@@ -11,7 +11,7 @@ import os
 import subprocess
 import threading
 
-IEF_ABI_VERSION = 1
+IEF_ABI_VERSION = 2
 IEF_MAX_ROWS = 64
 
 IEF_BF16, IEF_F16, IEF_F32 = 0, 1, 2
@@ -52,7 +52,7 @@ class CrossParams(C.Structure):
         ("mode", C.c_int32),
         ("base_row", C.POINTER(C.c_int32)), ("edit_slot", C.POINTER(C.c_int32)),
         ("n_slots", C.c_int32),
-        ("mapper", C.c_void_p), ("mapper_idx", C.c_void_p), ("refine_alpha", C.c_void_p),
+        ("mapper", C.c_void_p), ("mapper_nz_idx", C.c_void_p), ("mapper_nz_w", C.c_void_p), ("mapper_idx", C.c_void_p), ("refine_alpha", C.c_void_p),
         ("equalizer", C.c_void_p), ("step_alpha", C.c_void_p),
         ("probs_out", C.c_void_p),
         ("probs_accum", C.c_int32),

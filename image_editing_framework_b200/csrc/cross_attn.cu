@@ -4,9 +4,17 @@
 //   -> AttentionControlEdit.forward (attention_base.py:113-125) -> replace_cross_attention
 //      (attention_control.py:15-16 replace, :28-31 refine, :42-46 reweight) -> bmm (register.py:50)
 //   and AttentionStore.forward's capture of the post-edit maps (attention_base.py:64-68)
-// by one kernel: the <=80 key probabilities of a 64-query tile live in shared memory (fp32), the edit is
-// applied there, the maps are (optionally) streamed to / accumulated into the store with coalesced
-// writes, and P'V runs on the tensor cores. HBM-bound (AI ~ 76 flop/B): Q and O are touched once.
+// by one kernel. HBM / latency bound (AI ~ 76 flop/B): Q and O are touched once.
+//
+// A CTA is 64 query rows of one (batch row, head); each of its 4 warps owns 16 rows and keeps their <= 80 probabilities
+// in mma.sync accumulator registers from QK^T to P'V (no shared-memory round trip). Edited rows first compute the BASE
+// row's probabilities for the same queries and park them in a per-warp fp32 staging area (only __syncwarp needed), then
+// apply the edit in registers:
+//     E = edit(base, P);  E *= equalizer;  P' = E * alpha + (1 - alpha) * P
+// The replace mapper is applied in its sparse form (a word swap touches 1-4 source tokens per target token); a dense
+// 77x77 fp32 multiply on the CUDA cores is kept as a fallback for mappers with more than 8 non-zeros in a column.
+// Maps are streamed to / accumulated into the store straight from the registers (each quad writes 32-byte pieces).
+// Shared memory is sized per mode (25 KB for plain rows at head_dim 40), so 4-8 CTAs are resident per SM.
 #include "mma_utils.cuh"
 #include <math.h>
 
@@ -14,15 +22,19 @@ using namespace mmau;
 
 namespace {
 
-constexpr int kBM = 64, kNKP = 80, kPLD = 81, kThreads = 128;
+constexpr int kBM = 64, kNKP = 80, kPLD = 81, kThreads = 128, kNZ = 8;
 constexpr float kLog2e = 1.4426950408889634f;
+
+enum : int { kPlain = 0, kEditGather = 1, kEditDense = 2 };  // shared-memory / code flavour of a launch
 
 struct CrossArgs {
   ief_tensor4 q, k, v, o;
   int32_t B, H, Nq, Nk, d, mode;
   float scale_log2;
-  const float* mapper;
-  const int32_t* mapper_idx;
+  const float* mapper;          // dense [slots, Nk, Nk]
+  const int32_t* mapper_nz_idx; // sparse [slots, Nk, kNZ] (source token per non-zero, -1 padded)
+  const float* mapper_nz_w;     // sparse [slots, Nk, kNZ]
+  const int32_t* mapper_idx;    // refine gather [slots, Nk]
   const float* refine_alpha;
   const float* equalizer;
   const float* step_alpha;
@@ -31,20 +43,13 @@ struct CrossArgs {
   int32_t base_row[IEF_MAX_ROWS], edit_slot[IEF_MAX_ROWS], store_slot[IEF_MAX_ROWS];
 };
 
-// softmax(scale * Q[row] K[row]^T) for this CTA's 64-query tile -> dst (fp32 [64][kPLD], cols >= Nk zero)
+// softmax(scale * Q[row] K[row]^T) of this warp's 16 queries as normalised fp32 accumulator fragments:
+// s[nb][0..1] = row g, columns nb*8 + 2t, +1;  s[nb][2..3] = row g+8. Columns >= Nk come out as 0.
 template <int DTYPE, int DP>
-__device__ __forceinline__ void tile_probs(const CrossArgs& a, int src_row, int h, int qt, typename ElemT<DTYPE>::T* sQ,
-                                           typename ElemT<DTYPE>::T* sK, float* dst, int tid) {
-  using T = typename ElemT<DTYPE>::T;
+__device__ __forceinline__ void warp_probs(const CrossArgs& a, const typename ElemT<DTYPE>::T* sQ, const typename ElemT<DTYPE>::T* sK,
+                                           float (&s)[kNKP / 8][4], int warp, int lane) {
   constexpr int LD = DP + 8, KS = DP / 16;
-  const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  __syncthreads();  // previous users of sQ/sK are done
-  const T* qg = reinterpret_cast<const T*>(a.q.ptr) + (int64_t)src_row * a.q.stride_b + (int64_t)h * a.q.stride_h;
-  const T* kg = reinterpret_cast<const T*>(a.k.ptr) + (int64_t)src_row * a.k.stride_b + (int64_t)h * a.k.stride_h;
-  load_tile<T, kBM, DP, LD, kThreads>(sQ, qg, a.q.stride_n, qt * kBM, a.Nq, a.d, tid);
-  load_tile<T, kNKP, DP, LD, kThreads>(sK, kg, a.k.stride_n, 0, a.Nk, a.d, tid);
-  __syncthreads();
-  float s[kNKP / 8][4];
+  const int t = lane & 3;
 #pragma unroll
   for (int i = 0; i < kNKP / 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
 #pragma unroll
@@ -81,19 +86,21 @@ __device__ __forceinline__ void tile_probs(const CrossArgs& a, int src_row, int 
     l1 += s[nb][2] + s[nb][3];
   }
   const float i0 = 1.f / quad_sum(l0), i1 = 1.f / quad_sum(l1);
-  float* d0 = dst + (warp * 16 + g) * kPLD;
-  float* d1 = d0 + 8 * kPLD;
 #pragma unroll
   for (int nb = 0; nb < kNKP / 8; ++nb) {
-    const int c = nb * 8 + 2 * t;
-    d0[c] = s[nb][0] * i0;
-    d0[c + 1] = s[nb][1] * i0;
-    d1[c] = s[nb][2] * i1;
-    d1[c + 1] = s[nb][3] * i1;
+    s[nb][0] *= i0; s[nb][1] *= i0; s[nb][2] *= i1; s[nb][3] *= i1;
   }
 }
 
-template <int DTYPE, int DP>
+template <int FLAVOUR, int DP> constexpr int cross_smem_bytes() {
+  int b = (kBM + 2 * kNKP) * (DP + 8) * 2;                       // Q, K, V tiles
+  if (FLAVOUR != kPlain) b += 4 * 16 * kPLD * 4;                  // per-warp base-probability staging
+  if (FLAVOUR == kEditGather) b += kNKP * kNZ * 8;                // sparse mapper (idx + weight)
+  if (FLAVOUR == kEditDense) b += kNKP * kNKP * 4;                // dense mapper
+  return b;
+}
+
+template <int DTYPE, int DP, int FLAVOUR>
 __global__ void __launch_bounds__(kThreads)
 cross_attn_edit_kernel(const __grid_constant__ CrossArgs a) {
   using E = ElemT<DTYPE>;
@@ -104,73 +111,124 @@ cross_attn_edit_kernel(const __grid_constant__ CrossArgs a) {
   T* sQ = reinterpret_cast<T*>(smem4);
   T* sK = sQ + kBM * LD;
   T* sV = sK + kNKP * LD;
-  float* sP = reinterpret_cast<float*>(sV + kNKP * LD);
-  float* sPb = sP + kBM * kPLD;
-  float* sM = sPb + kBM * kPLD;
+  float* sPb = reinterpret_cast<float*>(sV + kNKP * LD);          // [4 warps][16][kPLD]   (edit flavours)
+  float* sM = sPb + 4 * 16 * kPLD;                                // dense mapper / sparse weights
+  int32_t* sMi = reinterpret_cast<int32_t*>(sM + kNKP * kNZ);     // sparse indices (gather flavour)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int base = a.base_row[b], slot = a.edit_slot[b], Nk = a.Nk;
+  const int base = FLAVOUR == kPlain ? -1 : a.base_row[b];
+  const int slot = a.edit_slot[b], Nk = a.Nk;
+  const bool edited = base >= 0;
 
-  if (base >= 0) {
-    if (a.mode == IEF_EDIT_REPLACE)
+  auto qptr = [&](int row) { return reinterpret_cast<const T*>(a.q.ptr) + (int64_t)row * a.q.stride_b + (int64_t)h * a.q.stride_h; };
+  auto kptr = [&](int row) { return reinterpret_cast<const T*>(a.k.ptr) + (int64_t)row * a.k.stride_b + (int64_t)h * a.k.stride_h; };
+  // V of this row is needed in both cases: fetch it with the first batch of loads
+  load_tile<T, kNKP, DP, LD, kThreads>(sV, reinterpret_cast<const T*>(a.v.ptr) + (int64_t)b * a.v.stride_b + (int64_t)h * a.v.stride_h, a.v.stride_n, 0, Nk,
+                                       a.d, tid);
+  float s[kNKP / 8][4];
+  float* wPb = sPb + warp * 16 * kPLD;
+  if (FLAVOUR != kPlain && edited) {
+    if (FLAVOUR == kEditDense && a.mode == IEF_EDIT_REPLACE)
       for (int i = tid; i < Nk * Nk; i += kThreads) sM[i] = __ldg(a.mapper + (int64_t)slot * Nk * Nk + i);
-    tile_probs<DTYPE, DP>(a, base, h, qt, sQ, sK, sPb, tid);
+    if (FLAVOUR == kEditGather && a.mode == IEF_EDIT_REPLACE)
+      for (int i = tid; i < Nk * kNZ; i += kThreads) {
+        sM[i] = __ldg(a.mapper_nz_w + (int64_t)slot * Nk * kNZ + i);
+        sMi[i] = __ldg(a.mapper_nz_idx + (int64_t)slot * Nk * kNZ + i);
+      }
+    load_tile<T, kBM, DP, LD, kThreads>(sQ, qptr(base), a.q.stride_n, qt * kBM, a.Nq, a.d, tid);
+    load_tile<T, kNKP, DP, LD, kThreads>(sK, kptr(base), a.k.stride_n, 0, Nk, a.d, tid);
+    __syncthreads();
+    warp_probs<DTYPE, DP>(a, sQ, sK, s, warp, lane);
+#pragma unroll
+    for (int nb = 0; nb < kNKP / 8; ++nb) {  // park the base probabilities of this warp's 16 rows
+      const int c = nb * 8 + 2 * t;
+      wPb[g * kPLD + c] = s[nb][0];
+      wPb[g * kPLD + c + 1] = s[nb][1];
+      wPb[(g + 8) * kPLD + c] = s[nb][2];
+      wPb[(g + 8) * kPLD + c + 1] = s[nb][3];
+    }
+    __syncthreads();  // every warp is done with the base row's Q/K tiles
   }
-  tile_probs<DTYPE, DP>(a, b, h, qt, sQ, sK, sP, tid);
-  {
-    const T* vg = reinterpret_cast<const T*>(a.v.ptr) + (int64_t)b * a.v.stride_b + (int64_t)h * a.v.stride_h;
-    load_tile<T, kNKP, DP, LD, kThreads>(sV, vg, a.v.stride_n, 0, Nk, a.d, tid);
-  }
+  load_tile<T, kBM, DP, LD, kThreads>(sQ, qptr(b), a.q.stride_n, qt * kBM, a.Nq, a.d, tid);
+  load_tile<T, kNKP, DP, LD, kThreads>(sK, kptr(b), a.k.stride_n, 0, Nk, a.d, tid);
   __syncthreads();
-  if (base >= 0) {
-    // P' = edit(base, P) * alpha + (1 - alpha) * P      (attention_base.py:119-120)
+  warp_probs<DTYPE, DP>(a, sQ, sK, s, warp, lane);
+
+  if (FLAVOUR != kPlain && edited) {
+    // P' = edit(base, P) * alpha + (1 - alpha) * P      (attention_base.py:119-120), in registers
     const float* al = a.step_alpha + (int64_t)slot * Nk;
     const float* eq = a.equalizer ? a.equalizer + (int64_t)slot * Nk : nullptr;
-    for (int i = tid; i < kBM * Nk; i += kThreads) {
-      const int r = i / Nk, n = i - r * Nk;
-      const float pb = sP[r * kPLD + n];
-      float e;
-      if (a.mode == IEF_EDIT_REPLACE) {
-        e = 0.f;
-        for (int w = 0; w < Nk; ++w) e = fmaf(sPb[r * kPLD + w], sM[w * Nk + n], e);
-      } else if (a.mode == IEF_EDIT_REFINE) {
-        int idx = __ldg(a.mapper_idx + (int64_t)slot * Nk + n);
-        if (idx < 0) idx += Nk;  // torch advanced indexing wraps -1 to the last column (attention_control.py:29)
-        const float ra = __ldg(a.refine_alpha + (int64_t)slot * Nk + n);
-        e = sPb[r * kPLD + idx] * ra + pb * (1.f - ra);
-      } else {
-        e = sPb[r * kPLD + n];
+#pragma unroll
+    for (int nb = 0; nb < kNKP / 8; ++nb) {
+#pragma unroll
+      for (int e2 = 0; e2 < 2; ++e2) {
+        const int n = nb * 8 + 2 * t + e2;
+        if (n < Nk) {
+          const float av = __ldg(al + n), eqv = eq ? __ldg(eq + n) : 1.f;
+          float ev[2];
+          if (a.mode == IEF_EDIT_REPLACE) {
+            ev[0] = ev[1] = 0.f;
+            if (FLAVOUR == kEditDense) {
+              for (int w = 0; w < Nk; ++w) {
+                const float m = sM[w * Nk + n];
+                ev[0] = fmaf(wPb[g * kPLD + w], m, ev[0]);
+                ev[1] = fmaf(wPb[(g + 8) * kPLD + w], m, ev[1]);
+              }
+            } else {
+#pragma unroll
+              for (int z = 0; z < kNZ; ++z) {
+                const int w = sMi[n * kNZ + z];
+                if (w >= 0) {
+                  const float m = sM[n * kNZ + z];
+                  ev[0] = fmaf(wPb[g * kPLD + w], m, ev[0]);
+                  ev[1] = fmaf(wPb[(g + 8) * kPLD + w], m, ev[1]);
+                }
+              }
+            }
+          } else if (a.mode == IEF_EDIT_REFINE) {
+            int idx = __ldg(a.mapper_idx + (int64_t)slot * Nk + n);
+            if (idx < 0) idx += Nk;  // torch advanced indexing wraps -1 to the last column (attention_control.py:29)
+            const float ra = __ldg(a.refine_alpha + (int64_t)slot * Nk + n);
+            ev[0] = wPb[g * kPLD + idx] * ra + s[nb][e2] * (1.f - ra);
+            ev[1] = wPb[(g + 8) * kPLD + idx] * ra + s[nb][2 + e2] * (1.f - ra);
+          } else {
+            ev[0] = wPb[g * kPLD + n];
+            ev[1] = wPb[(g + 8) * kPLD + n];
+          }
+          s[nb][e2] = ev[0] * eqv * av + (1.f - av) * s[nb][e2];
+          s[nb][2 + e2] = ev[1] * eqv * av + (1.f - av) * s[nb][2 + e2];
+        }
       }
-      if (eq) e *= __ldg(eq + n);
-      const float av = __ldg(al + n);
-      sP[r * kPLD + n] = e * av + (1.f - av) * pb;
     }
-    __syncthreads();
   }
+  const int grow0 = qt * kBM + warp * 16 + g;
   const int sslot = a.store_slot[b];
   if (a.probs != nullptr && sslot >= 0) {
-    // rows of this tile are contiguous in the [slot, H, Nq, Nk] store: fully coalesced
-    const int rows = min(kBM, a.Nq - qt * kBM);
-    float* dst = a.probs + (((int64_t)sslot * a.H + h) * a.Nq + (int64_t)qt * kBM) * Nk;
-    for (int i = tid; i < rows * Nk; i += kThreads) {
-      const int r = i / Nk, n = i - r * Nk;
-      const float v = sP[r * kPLD + n];
-      dst[i] = a.probs_accum ? dst[i] + v : v;
+    // post-edit maps -> store (overwrite or accumulate); each quad covers 8 consecutive floats of a row
+    float* p0 = a.probs + (((int64_t)sslot * a.H + h) * a.Nq + grow0) * Nk;
+    float* p1 = p0 + (int64_t)8 * Nk;
+#pragma unroll
+    for (int nb = 0; nb < kNKP / 8; ++nb) {
+#pragma unroll
+      for (int e2 = 0; e2 < 2; ++e2) {
+        const int n = nb * 8 + 2 * t + e2;
+        if (n < Nk) {
+          if (grow0 < a.Nq) p0[n] = a.probs_accum ? p0[n] + s[nb][e2] : s[nb][e2];
+          if (grow0 + 8 < a.Nq) p1[n] = a.probs_accum ? p1[n] + s[nb][2 + e2] : s[nb][2 + e2];
+        }
+      }
     }
   }
-  // O = P' V
+  // O = P' V  (probabilities straight from the accumulator fragments)
   float o[NB][4];
 #pragma unroll
   for (int i = 0; i < NB; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
-  const float* p0 = sP + (warp * 16 + g) * kPLD;
-  const float* p1 = p0 + 8 * kPLD;
 #pragma unroll
   for (int kk = 0; kk < kNKP / 16; ++kk) {
-    const int c = kk * 16 + 2 * t;
     uint32_t pa[4];
-    pa[0] = E::pack(p0[c], p0[c + 1]);
-    pa[1] = E::pack(p1[c], p1[c + 1]);
-    pa[2] = E::pack(p0[c + 8], p0[c + 9]);
-    pa[3] = E::pack(p1[c + 8], p1[c + 9]);
+    pa[0] = E::pack(s[2 * kk][0], s[2 * kk][1]);
+    pa[1] = E::pack(s[2 * kk][2], s[2 * kk][3]);
+    pa[2] = E::pack(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+    pa[3] = E::pack(s[2 * kk + 1][2], s[2 * kk + 1][3]);
 #pragma unroll
     for (int nb2 = 0; nb2 < KS; ++nb2) {
       uint32_t vf[4];
@@ -179,7 +237,6 @@ cross_attn_edit_kernel(const __grid_constant__ CrossArgs a) {
       mma16816<DTYPE>(o[2 * nb2 + 1], pa, vf[2], vf[3]);
     }
   }
-  const int grow0 = qt * kBM + warp * 16 + g;
   T* og = reinterpret_cast<T*>(a.o.ptr) + (int64_t)b * a.o.stride_b + (int64_t)h * a.o.stride_h;
 #pragma unroll
   for (int nb = 0; nb < NB; ++nb) {
@@ -191,10 +248,10 @@ cross_attn_edit_kernel(const __grid_constant__ CrossArgs a) {
   }
 }
 
-template <int DTYPE, int DP>
+template <int DTYPE, int DP, int FLAVOUR>
 int launch_one(const CrossArgs& a, dim3 grid, cudaStream_t st) {
-  constexpr int smem = (kBM + 2 * kNKP) * (DP + 8) * 2 + 2 * kBM * kPLD * 4 + kNKP * kNKP * 4;
-  auto kern = cross_attn_edit_kernel<DTYPE, DP>;
+  constexpr int smem = cross_smem_bytes<FLAVOUR, DP>();
+  auto kern = cross_attn_edit_kernel<DTYPE, DP, FLAVOUR>;
   static bool configured = false;
   if (!configured) {
     IEF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -205,16 +262,23 @@ int launch_one(const CrossArgs& a, dim3 grid, cudaStream_t st) {
   return IEF_OK;
 }
 
-template <int DTYPE>
+template <int DTYPE, int FLAVOUR>
 int launch_dp(const CrossArgs& a, dim3 grid, cudaStream_t st) {
   const int d = a.d;
-  if (d <= 32) return launch_one<DTYPE, 32>(a, grid, st);
-  if (d <= 48) return launch_one<DTYPE, 48>(a, grid, st);
-  if (d <= 64) return launch_one<DTYPE, 64>(a, grid, st);
-  if (d <= 80) return launch_one<DTYPE, 80>(a, grid, st);
-  if (d <= 96) return launch_one<DTYPE, 96>(a, grid, st);
-  if (d <= 128) return launch_one<DTYPE, 128>(a, grid, st);
-  return launch_one<DTYPE, 160>(a, grid, st);
+  if (d <= 32) return launch_one<DTYPE, 32, FLAVOUR>(a, grid, st);
+  if (d <= 48) return launch_one<DTYPE, 48, FLAVOUR>(a, grid, st);
+  if (d <= 64) return launch_one<DTYPE, 64, FLAVOUR>(a, grid, st);
+  if (d <= 80) return launch_one<DTYPE, 80, FLAVOUR>(a, grid, st);
+  if (d <= 96) return launch_one<DTYPE, 96, FLAVOUR>(a, grid, st);
+  if (d <= 128) return launch_one<DTYPE, 128, FLAVOUR>(a, grid, st);
+  return launch_one<DTYPE, 160, FLAVOUR>(a, grid, st);
+}
+
+template <int DTYPE>
+int launch_flavour(const CrossArgs& a, int flavour, dim3 grid, cudaStream_t st) {
+  if (flavour == kPlain) return launch_dp<DTYPE, kPlain>(a, grid, st);
+  if (flavour == kEditGather) return launch_dp<DTYPE, kEditGather>(a, grid, st);
+  return launch_dp<DTYPE, kEditDense>(a, grid, st);
 }
 
 }  // namespace
@@ -236,7 +300,8 @@ extern "C" int ief_cross_attn_edit_fwd(const ief_cross_params* p, void* stream) 
   a.q = p->q; a.k = p->k; a.v = p->v; a.o = p->o;
   a.B = p->B; a.H = p->H; a.Nq = p->Nq; a.Nk = p->Nk; a.d = p->d; a.mode = p->mode;
   a.scale_log2 = p->scale * kLog2e;
-  a.mapper = p->mapper; a.mapper_idx = p->mapper_idx; a.refine_alpha = p->refine_alpha;
+  a.mapper = p->mapper; a.mapper_nz_idx = p->mapper_nz_idx; a.mapper_nz_w = p->mapper_nz_w;
+  a.mapper_idx = p->mapper_idx; a.refine_alpha = p->refine_alpha;
   a.equalizer = p->equalizer; a.step_alpha = p->step_alpha;
   a.probs = p->probs_out; a.probs_accum = p->probs_accum;
   bool any_edit = false;
@@ -250,14 +315,17 @@ extern "C" int ief_cross_attn_edit_fwd(const ief_cross_params* p, void* stream) 
       IEF_REQUIRE(a.edit_slot[i] >= 0 && a.edit_slot[i] < p->n_slots, IEF_ERR_INVALID, "ief_cross_attn_edit_fwd: edit_slot[%d] out of range", i);
     }
   }
+  int flavour = kPlain;
   if (any_edit) {
     IEF_REQUIRE(p->step_alpha != nullptr, IEF_ERR_INVALID, "ief_cross_attn_edit_fwd: step_alpha required when a row is edited");
-    IEF_REQUIRE(p->mode != IEF_EDIT_REPLACE || p->mapper, IEF_ERR_INVALID, "ief_cross_attn_edit_fwd: mapper required for REPLACE");
+    IEF_REQUIRE(p->mode >= IEF_EDIT_NONE && p->mode <= IEF_EDIT_REFINE, IEF_ERR_INVALID, "ief_cross_attn_edit_fwd: bad mode %d", p->mode);
+    IEF_REQUIRE(p->mode != IEF_EDIT_REPLACE || p->mapper || (p->mapper_nz_idx && p->mapper_nz_w), IEF_ERR_INVALID,
+                "ief_cross_attn_edit_fwd: REPLACE needs mapper or mapper_nz_idx + mapper_nz_w");
     IEF_REQUIRE(p->mode != IEF_EDIT_REFINE || (p->mapper_idx && p->refine_alpha), IEF_ERR_INVALID,
                 "ief_cross_attn_edit_fwd: mapper_idx and refine_alpha required for REFINE");
-    IEF_REQUIRE(p->mode >= IEF_EDIT_NONE && p->mode <= IEF_EDIT_REFINE, IEF_ERR_INVALID, "ief_cross_attn_edit_fwd: bad mode %d", p->mode);
+    flavour = (p->mode == IEF_EDIT_REPLACE && !(p->mapper_nz_idx && p->mapper_nz_w)) ? kEditDense : kEditGather;
   }
   dim3 grid(ief_ceil_div(p->Nq, kBM), p->H, p->B);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  return p->dtype == IEF_BF16 ? launch_dp<IEF_BF16>(a, grid, st) : launch_dp<IEF_F16>(a, grid, st);
+  return p->dtype == IEF_BF16 ? launch_flavour<IEF_BF16>(a, flavour, grid, st) : launch_flavour<IEF_F16>(a, flavour, grid, st);
 }

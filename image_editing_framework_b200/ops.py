@@ -96,9 +96,32 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, sca
 class CrossEdit:
     """Device-side tables of one P2P cross-attention edit (built once per controller)."""
 
-    def __init__(self, mode: int, n_slots: int, mapper=None, mapper_idx=None, refine_alpha=None, equalizer=None):
+    MAX_NZ = 8  # kNZ in csrc/cross_attn.cu
+
+    def __init__(self, mode: int, n_slots: int, mapper=None, mapper_idx=None, refine_alpha=None, equalizer=None,
+                 mapper_nz_idx=None, mapper_nz_w=None):
         self.mode, self.n_slots = mode, n_slots
         self.mapper, self.mapper_idx, self.refine_alpha, self.equalizer = mapper, mapper_idx, refine_alpha, equalizer
+        self.mapper_nz_idx, self.mapper_nz_w = mapper_nz_idx, mapper_nz_w
+        if mode == IEF_EDIT_REPLACE and mapper is not None and mapper_nz_idx is None:
+            self.mapper_nz_idx, self.mapper_nz_w = self.sparsify(mapper)
+
+    @classmethod
+    def sparsify(cls, mapper: torch.Tensor):
+        """Sparse form of a [slots, Nk, Nk] replacement mapper: per target token the (<= 8) contributing source tokens in
+        ascending order. Returns (None, None) when a column has more non-zeros (the kernel then multiplies the dense form)."""
+        m = mapper.detach().float().cpu()
+        slots, nk, _ = m.shape
+        idx = torch.full((slots, nk, cls.MAX_NZ), -1, dtype=torch.int32)
+        w = torch.zeros((slots, nk, cls.MAX_NZ), dtype=torch.float32)
+        for s_ in range(slots):
+            for n in range(nk):
+                nz = torch.nonzero(m[s_, :, n], as_tuple=False).flatten()
+                if nz.numel() > cls.MAX_NZ:
+                    return None, None
+                idx[s_, n, :nz.numel()] = nz.to(torch.int32)
+                w[s_, n, :nz.numel()] = m[s_, nz, n]
+        return idx.to(mapper.device).contiguous(), w.to(mapper.device).contiguous()
 
 
 def cross_attention_edit(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, scale: float, *,
@@ -124,11 +147,11 @@ def cross_attention_edit(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, head
     p.base_row, p.edit_slot, p.store_slot = [C.cast(x, C.POINTER(C.c_int32)) if x is not None else None for x in keep]
     if edit is not None:
         p.mode, p.n_slots = edit.mode, edit.n_slots
-        for name in ("mapper", "mapper_idx", "refine_alpha", "equalizer"):
+        for name in ("mapper", "mapper_nz_idx", "mapper_nz_w", "mapper_idx", "refine_alpha", "equalizer"):
             t = getattr(edit, name)
             if t is not None:
                 _require_cuda(t)
-                want = torch.int32 if name == "mapper_idx" else torch.float32
+                want = torch.int32 if name in ("mapper_idx", "mapper_nz_idx") else torch.float32
                 if t.dtype != want or not t.is_contiguous():
                     raise TypeError(f"CrossEdit.{name} must be contiguous {want}")
                 setattr(p, name, t.data_ptr())

@@ -59,4 +59,4 @@ class AttentionReweight(AttentionControlEdit):
         else:
             e = ops.CrossEdit(ops.IEF_EDIT_NONE, n)
         return ops.CrossEdit(e.mode, n, mapper=e.mapper, mapper_idx=e.mapper_idx, refine_alpha=e.refine_alpha,
-                             equalizer=self.equalizer.to(torch.float32).contiguous())
+                             equalizer=self.equalizer.to(torch.float32).contiguous(), mapper_nz_idx=e.mapper_nz_idx, mapper_nz_w=e.mapper_nz_w)

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define IEF_ABI_VERSION 1
+#define IEF_ABI_VERSION 2
 #define IEF_MAX_ROWS 64  /* max UNet batch rows per call (reference uses 1, 2 or 4) */
 #define IEF_MAX_WORDS 77 /* CLIP context length, p2p/model/ptp_utils.py:8 MAX_NUM_WORDS */
 
@@ -119,7 +119,12 @@ typedef struct ief_cross_params {
   const int32_t* base_row;  /* HOST [B]; NULL = no edit on any row */
   const int32_t* edit_slot; /* HOST [B]; NULL = slot 0 */
   int32_t n_slots;
-  const float* mapper;       /* device fp32 [n_slots, Nk, Nk]  (REPLACE) */
+  const float* mapper;       /* device fp32 [n_slots, Nk, Nk]  (REPLACE, dense form) */
+  const int32_t* mapper_nz_idx; /* optional sparse form of mapper: device int32 [n_slots, Nk, 8], for target token n the source
+                                   tokens w with mapper[w][n] != 0 in ascending order, padded with -1 (a word swap touches a
+                                   handful of tokens). When given (with mapper_nz_w) it is used instead of the dense form and
+                                   yields bit-identical results; a column with more than 8 non-zeros needs the dense form. */
+  const float* mapper_nz_w;     /* device fp32 [n_slots, Nk, 8]: the matching mapper[w][n] values */
   const int32_t* mapper_idx; /* device int32 [n_slots, Nk], may hold -1 (REFINE; -1 wraps to Nk-1 as torch indexing does) */
   const float* refine_alpha; /* device fp32 [n_slots, Nk]      (REFINE) */
   const float* equalizer;    /* device fp32 [n_slots, Nk] or NULL */
