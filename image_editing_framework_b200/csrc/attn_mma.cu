@@ -37,45 +37,60 @@ attn_mma_kernel(const __grid_constant__ MmaArgs a) {
   if (!a.rows.active[b]) return;
   extern __shared__ uint4 smem4[];
   T* sQ = reinterpret_cast<T*>(smem4);
-  T* sK = sQ + kBM * LD;
-  T* sV = sK + kBN * LD;
+  T* sKV = sQ + kBM * LD;  // two stages of [K tile | V tile]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int nk_total = a.Nk * (a.nt2 > 0 ? 2 : 1);
+  const int nt = a.nt1 + a.nt2;
+  constexpr int NSWEEP = WRITE_P ? 2 : 1;
+  const int n_iter = NSWEEP * nt;
+
+  // key/value tile `it` of the flattened (sweep, tile) sequence -> stage it & 1, by cp.async (the statistics sweep needs no V)
+  auto fetch = [&](int it) {
+    const int j = it >= nt ? it - nt : it;
+    const bool blk2 = j >= a.nt1;
+    const int jj = blk2 ? j - a.nt1 : j;
+    const int kb = blk2 ? a.rows.k2[b] : a.rows.k[b];
+    const int vb = blk2 ? a.rows.v2[b] : a.rows.v[b];
+    T* sK = sKV + (it & 1) * 2 * kBN * LD;
+    const T* kg = reinterpret_cast<const T*>(a.k.ptr) + (int64_t)kb * a.k.stride_b + (int64_t)h * a.k.stride_h;
+    load_tile_async<T, kBN, DP, LD, kThreads>(sK, kg, a.k.stride_n, jj * kBN, a.Nk, a.d, tid);
+    if (!(WRITE_P && it < nt)) {
+      const T* vg = reinterpret_cast<const T*>(a.v.ptr) + (int64_t)vb * a.v.stride_b + (int64_t)h * a.v.stride_h;
+      load_tile_async<T, kBN, DP, LD, kThreads>(sK + kBN * LD, vg, a.v.stride_n, jj * kBN, a.Nk, a.d, tid);
+    }
+    cp_async_commit();
+  };
 
   const T* qg = reinterpret_cast<const T*>(a.q.ptr) + (int64_t)a.rows.q[b] * a.q.stride_b + (int64_t)h * a.q.stride_h;
-  load_tile<T, kBM, DP, LD, kThreads>(sQ, qg, a.q.stride_n, qt * kBM, a.Nq, a.d, tid);
-  __syncthreads();
+  load_tile_async<T, kBM, DP, LD, kThreads>(sQ, qg, a.q.stride_n, qt * kBM, a.Nq, a.d, tid);
+  fetch(0);
   uint32_t qf[KS][4];
-#pragma unroll
-  for (int kk = 0; kk < KS; ++kk) ldsm_x4(qf[kk], &sQ[(warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LD + kk * 16 + (lane >> 4) * 8]);
 
   float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f}, inv_l[2] = {1.f, 1.f};
   float o[NB][4];
 #pragma unroll
   for (int i = 0; i < NB; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
   const float c2 = a.scale_log2;
-  const int nt = a.nt1 + a.nt2;
   const int grow0 = qt * kBM + warp * 16 + g;  // rows grow0 and grow0 + 8
 
-  constexpr int NSWEEP = WRITE_P ? 2 : 1;
 #pragma unroll 1
-  for (int sweep = 0; sweep < NSWEEP; ++sweep) {
-    const bool stats_only = WRITE_P && sweep == 0;
-    const bool emit = WRITE_P && sweep == 1;
-#pragma unroll 1
-    for (int j = 0; j < nt; ++j) {
+  for (int it = 0; it < n_iter; ++it) {
+    const int sweep = it >= nt ? 1 : 0;
+    const int j = it - sweep * nt;
+    {
+      const bool stats_only = WRITE_P && sweep == 0;
+      const bool emit = WRITE_P && sweep == 1;
       const bool blk2 = j >= a.nt1;
       const int jj = blk2 ? j - a.nt1 : j;
-      const int kb = blk2 ? a.rows.k2[b] : a.rows.k[b];
-      const int vb = blk2 ? a.rows.v2[b] : a.rows.v[b];
-      __syncthreads();
-      const T* kg = reinterpret_cast<const T*>(a.k.ptr) + (int64_t)kb * a.k.stride_b + (int64_t)h * a.k.stride_h;
-      load_tile<T, kBN, DP, LD, kThreads>(sK, kg, a.k.stride_n, jj * kBN, a.Nk, a.d, tid);
-      if (!stats_only) {
-        const T* vg = reinterpret_cast<const T*>(a.v.ptr) + (int64_t)vb * a.v.stride_b + (int64_t)h * a.v.stride_h;
-        load_tile<T, kBN, DP, LD, kThreads>(sV, vg, a.v.stride_n, jj * kBN, a.Nk, a.d, tid);
+      const T* sK = sKV + (it & 1) * 2 * kBN * LD;
+      const T* sV = sK + kBN * LD;
+      cp_async_wait<0>();
+      __syncthreads();                    // tile `it` has landed; every warp is done with tile it-1
+      if (it + 1 < n_iter) fetch(it + 1);  // overlaps with the math below
+      if (it == 0) {
+#pragma unroll
+        for (int kk = 0; kk < KS; ++kk) ldsm_x4(qf[kk], &sQ[(warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LD + kk * 16 + (lane >> 4) * 8]);
       }
-      __syncthreads();
       // S = Q K^T  (16 rows x 64 keys per warp)
       float s[8][4];
 #pragma unroll
@@ -171,7 +186,7 @@ attn_mma_kernel(const __grid_constant__ MmaArgs a) {
         }
       }
     }
-    if (sweep == 0) {
+    if (it == nt - 1) {  // end of the first (or only) sweep
       l[0] = quad_sum(l[0]);
       l[1] = quad_sum(l[1]);
       if (WRITE_P) { inv_l[0] = 1.f / l[0]; inv_l[1] = 1.f / l[1]; }
@@ -191,7 +206,7 @@ attn_mma_kernel(const __grid_constant__ MmaArgs a) {
 
 template <int DTYPE, int DP, bool WRITE_P>
 int launch_one(const MmaArgs& a, dim3 grid, cudaStream_t st) {
-  constexpr int smem = (kBM + 2 * kBN) * (DP + 8) * 2;
+  constexpr int smem = (kBM + 4 * kBN) * (DP + 8) * 2;  // Q + two stages of K, V
   auto kern = attn_mma_kernel<DTYPE, DP, WRITE_P>;
   static bool configured = false;
   if (!configured) {

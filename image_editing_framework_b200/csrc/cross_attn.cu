@@ -94,6 +94,7 @@ __device__ __forceinline__ void warp_probs(const CrossArgs& a, const typename El
 
 template <int FLAVOUR, int DP> constexpr int cross_smem_bytes() {
   int b = (kBM + 2 * kNKP) * (DP + 8) * 2;                       // Q, K, V tiles
+  if (FLAVOUR != kPlain) b += (kBM + kNKP) * (DP + 8) * 2;        // base row's Q, K tiles (fetched in the same round trip)
   if (FLAVOUR != kPlain) b += 4 * 16 * kPLD * 4;                  // per-warp base-probability staging
   if (FLAVOUR == kEditGather) b += kNKP * kNZ * 8;                // sparse mapper (idx + weight)
   if (FLAVOUR == kEditDense) b += kNKP * kNKP * 4;                // dense mapper
@@ -111,7 +112,9 @@ cross_attn_edit_kernel(const __grid_constant__ CrossArgs a) {
   T* sQ = reinterpret_cast<T*>(smem4);
   T* sK = sQ + kBM * LD;
   T* sV = sK + kNKP * LD;
-  float* sPb = reinterpret_cast<float*>(sV + kNKP * LD);          // [4 warps][16][kPLD]   (edit flavours)
+  T* sQb = sV + kNKP * LD;                                        // base row's tiles (edit flavours)
+  T* sKb = sQb + kBM * LD;
+  float* sPb = reinterpret_cast<float*>(FLAVOUR == kPlain ? sQb : sKb + kNKP * LD);  // [4 warps][16][kPLD]   (edit flavours)
   float* sM = sPb + 4 * 16 * kPLD;                                // dense mapper / sparse weights
   int32_t* sMi = reinterpret_cast<int32_t*>(sM + kNKP * kNZ);     // sparse indices (gather flavour)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
@@ -121,9 +124,18 @@ cross_attn_edit_kernel(const __grid_constant__ CrossArgs a) {
 
   auto qptr = [&](int row) { return reinterpret_cast<const T*>(a.q.ptr) + (int64_t)row * a.q.stride_b + (int64_t)h * a.q.stride_h; };
   auto kptr = [&](int row) { return reinterpret_cast<const T*>(a.k.ptr) + (int64_t)row * a.k.stride_b + (int64_t)h * a.k.stride_h; };
-  // V of this row is needed in both cases: fetch it with the first batch of loads
-  load_tile<T, kNKP, DP, LD, kThreads>(sV, reinterpret_cast<const T*>(a.v.ptr) + (int64_t)b * a.v.stride_b + (int64_t)h * a.v.stride_h, a.v.stride_n, 0, Nk,
-                                       a.d, tid);
+  // Every tile this CTA needs is requested up front with cp.async: group 0 = the base row's Q/K (edited rows), group 1 = own
+  // Q/K/V. One memory round trip per CTA; the base probabilities are computed while group 1 is still landing.
+  if (FLAVOUR != kPlain && edited) {
+    load_tile_async<T, kBM, DP, LD, kThreads>(sQb, qptr(base), a.q.stride_n, qt * kBM, a.Nq, a.d, tid);
+    load_tile_async<T, kNKP, DP, LD, kThreads>(sKb, kptr(base), a.k.stride_n, 0, Nk, a.d, tid);
+  }
+  cp_async_commit();
+  load_tile_async<T, kBM, DP, LD, kThreads>(sQ, qptr(b), a.q.stride_n, qt * kBM, a.Nq, a.d, tid);
+  load_tile_async<T, kNKP, DP, LD, kThreads>(sK, kptr(b), a.k.stride_n, 0, Nk, a.d, tid);
+  load_tile_async<T, kNKP, DP, LD, kThreads>(sV, reinterpret_cast<const T*>(a.v.ptr) + (int64_t)b * a.v.stride_b + (int64_t)h * a.v.stride_h, a.v.stride_n, 0,
+                                             Nk, a.d, tid);
+  cp_async_commit();
   float s[kNKP / 8][4];
   float* wPb = sPb + warp * 16 * kPLD;
   if (FLAVOUR != kPlain && edited) {
@@ -134,22 +146,19 @@ cross_attn_edit_kernel(const __grid_constant__ CrossArgs a) {
         sM[i] = __ldg(a.mapper_nz_w + (int64_t)slot * Nk * kNZ + i);
         sMi[i] = __ldg(a.mapper_nz_idx + (int64_t)slot * Nk * kNZ + i);
       }
-    load_tile<T, kBM, DP, LD, kThreads>(sQ, qptr(base), a.q.stride_n, qt * kBM, a.Nq, a.d, tid);
-    load_tile<T, kNKP, DP, LD, kThreads>(sK, kptr(base), a.k.stride_n, 0, Nk, a.d, tid);
+    cp_async_wait<1>();
     __syncthreads();
-    warp_probs<DTYPE, DP>(a, sQ, sK, s, warp, lane);
+    warp_probs<DTYPE, DP>(a, sQb, sKb, s, warp, lane);
 #pragma unroll
-    for (int nb = 0; nb < kNKP / 8; ++nb) {  // park the base probabilities of this warp's 16 rows
+    for (int nb = 0; nb < kNKP / 8; ++nb) {  // park the base probabilities of this warp's 16 rows (read back by this warp only)
       const int c = nb * 8 + 2 * t;
       wPb[g * kPLD + c] = s[nb][0];
       wPb[g * kPLD + c + 1] = s[nb][1];
       wPb[(g + 8) * kPLD + c] = s[nb][2];
       wPb[(g + 8) * kPLD + c + 1] = s[nb][3];
     }
-    __syncthreads();  // every warp is done with the base row's Q/K tiles
   }
-  load_tile<T, kBM, DP, LD, kThreads>(sQ, qptr(b), a.q.stride_n, qt * kBM, a.Nq, a.d, tid);
-  load_tile<T, kNKP, DP, LD, kThreads>(sK, kptr(b), a.k.stride_n, 0, Nk, a.d, tid);
+  cp_async_wait<0>();
   __syncthreads();
   warp_probs<DTYPE, DP>(a, sQ, sK, s, warp, lane);
 

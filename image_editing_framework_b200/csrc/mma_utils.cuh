@@ -39,6 +39,27 @@ __device__ __forceinline__ void load_tile(T* s, const T* g, int64_t g_row_stride
   }
 }
 
+// Same tile copy with cp.async (LDGSTS): no register staging, every 16-byte piece of the tile is in flight at once, so a
+// tile costs one memory round trip instead of one per loop iteration. Out-of-range pieces are zero-filled (src-size 0).
+// Complete with cp_async_commit() + cp_async_wait<N>() + a barrier.
+template <typename T, int ROWS, int DP, int LD, int NTHREADS>
+__device__ __forceinline__ void load_tile_async(T* s, const T* g, int64_t g_row_stride, int row0, int n_valid, int d, int tid) {
+  constexpr int CPR = DP / 8;
+#pragma unroll
+  for (int i0 = 0; i0 < ROWS * CPR; i0 += NTHREADS) {
+    const int i = i0 + tid;
+    if (i < ROWS * CPR) {
+      const int r = i / CPR, c = (i % CPR) * 8;
+      const bool ok = row0 + r < n_valid && c < d;
+      const T* src = ok ? g + (int64_t)(row0 + r) * g_row_stride + c : g;
+      const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(s + r * LD + c));
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0) : "memory");
+    }
+  }
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 __device__ __forceinline__ float quad_max(float v) {
   v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
   v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));

@@ -1,5 +1,6 @@
 """CUDA-event timings of the HBM / latency-bound kernels at SD-1.5 shapes, with algorithmic bytes and GB/s against the measured
-copy bandwidth (MEASURED_PEAKS.json hbm_gbs). L2 is flushed between repetitions."""
+copy bandwidth (MEASURED_PEAKS.json hbm_gbs). L2 is flushed between repetitions and the call is enqueued behind a
+spin kernel, so the events bracket device time only (not the Python/ctypes call overhead)."""
 import json
 import os
 import sys
@@ -21,6 +22,7 @@ def time_call(fn, reps=20, warm=5):
     ts = []
     for _ in range(reps):
         flush.zero_()
+        torch.cuda._sleep(400000)  # keep the GPU busy while the host builds the call, so the events bracket the kernel only
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         fn()
