@@ -11,7 +11,7 @@ import os
 import subprocess
 import threading
 
-IEF_ABI_VERSION = 2
+IEF_ABI_VERSION = 3
 IEF_MAX_ROWS = 64
 
 IEF_BF16, IEF_F16, IEF_F32 = 0, 1, 2
@@ -40,6 +40,9 @@ class AttnParams(C.Structure):
         ("probs_accum", C.c_int32),
         ("probs_slot", C.POINTER(C.c_int32)),
         ("row_mask", C.POINTER(C.c_uint8)),
+        ("key_bias", C.c_void_p),
+        ("bias_sel", C.POINTER(C.c_int32)),
+        ("n_bias", C.c_int32),
     ]
 
 
@@ -83,7 +86,7 @@ class UmmaProbeParams(C.Structure):
 
 # every symbol include/ief_b200.h declares; tests check the .so exports each one
 EXPORTS = (
-    "ief_attn_fwd", "ief_cross_attn_edit_fwd", "ief_store_accumulate", "ief_local_blend", "ief_cfg_ddim_step",
+    "ief_attn_fwd", "ief_cross_attn_edit_fwd", "ief_store_accumulate", "ief_local_blend", "ief_mask_blend", "ief_cfg_ddim_step",
     "ief_umma_probe", "ief_abi_version", "ief_last_error", "ief_launch_count", "ief_last_attn_impl", "ief_check_device",
 )
 
@@ -148,6 +151,9 @@ def lib() -> C.CDLL:
         L.ief_cfg_ddim_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                         C.c_float, C.c_float, C.c_float, C.c_void_p]
         L.ief_cfg_ddim_step.restype = C.c_int
+        L.ief_mask_blend.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int64,
+                                     C.POINTER(C.c_uint8), C.c_void_p]
+        L.ief_mask_blend.restype = C.c_int
         L.ief_umma_probe.argtypes = [C.POINTER(UmmaProbeParams), C.c_void_p]
         L.ief_umma_probe.restype = C.c_int
         if L.ief_abi_version() != IEF_ABI_VERSION:

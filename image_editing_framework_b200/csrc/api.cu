@@ -47,6 +47,7 @@ extern "C" int ief_attn_fwd(const ief_attn_params* p, void* stream) {
   IEF_REQUIRE(p->d >= 8, IEF_ERR_INVALID, "ief_attn_fwd: head_dim %d", p->d);
   IEF_REQUIRE(p->scale > 0.f, IEF_ERR_INVALID, "ief_attn_fwd: scale must be positive");
   IefRowTable rows;
+  bool any_bias = false;
   for (int i = 0; i < p->B; ++i) {
     rows.q[i] = p->q_src ? p->q_src[i] : i;
     rows.k[i] = p->k_src ? p->k_src[i] : i;
@@ -55,6 +56,9 @@ extern "C" int ief_attn_fwd(const ief_attn_params* p, void* stream) {
     rows.v2[i] = p->v_src2 ? p->v_src2[i] : -1;
     rows.pslot[i] = p->probs_slot ? p->probs_slot[i] : i;
     rows.active[i] = p->row_mask ? p->row_mask[i] : 1;
+    rows.bias[i] = (p->key_bias && p->bias_sel) ? p->bias_sel[i] : -1;
+    IEF_REQUIRE(rows.bias[i] < p->n_bias, IEF_ERR_INVALID, "ief_attn_fwd: bias_sel[%d]=%d but n_bias=%d", i, rows.bias[i], p->n_bias);
+    if (rows.bias[i] >= 0) any_bias = true;
     IEF_REQUIRE(rows.q[i] >= 0 && rows.q[i] < p->B && rows.k[i] >= 0 && rows.k[i] < p->B && rows.v[i] >= 0 && rows.v[i] < p->B,
                 IEF_ERR_INVALID, "ief_attn_fwd: source row index out of range for row %d", i);
     IEF_REQUIRE(rows.k2[i] < p->B && rows.v2[i] < p->B, IEF_ERR_INVALID, "ief_attn_fwd: second-block row index out of range for row %d", i);
@@ -62,13 +66,18 @@ extern "C" int ief_attn_fwd(const ief_attn_params* p, void* stream) {
   }
   for (int i = p->B; i < IEF_MAX_ROWS; ++i) {
     rows.q[i] = rows.k[i] = rows.v[i] = 0;
-    rows.k2[i] = rows.v2[i] = rows.pslot[i] = -1;
+    rows.k2[i] = rows.v2[i] = rows.pslot[i] = rows.bias[i] = -1;
     rows.active[i] = 0;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int impl = p->impl;
   if (p->probs_out) {
     IEF_REQUIRE(impl != IEF_IMPL_TCGEN05, IEF_ERR_UNSUPPORTED, "ief_attn_fwd: probs_out is only produced by the mma kernel");
+    impl = IEF_IMPL_MMA;
+  }
+  if (any_bias) {
+    IEF_REQUIRE(impl != IEF_IMPL_TCGEN05, IEF_ERR_UNSUPPORTED, "ief_attn_fwd: key_bias is only implemented by the mma kernel");
+    IEF_REQUIRE(p->k_src2 == nullptr, IEF_ERR_UNSUPPORTED, "ief_attn_fwd: key_bias cannot be combined with a second key/value block");
     impl = IEF_IMPL_MMA;
   }
   if (impl == IEF_IMPL_AUTO) {

@@ -22,6 +22,7 @@ struct MmaArgs {
   float scale_log2;
   float* probs;         // [B,H,Nq,Nk_total] or null
   int32_t probs_accum;
+  const float* key_bias;  // [n_bias, Nk] additive bias on the scaled scores, or null
   IefRowTable rows;
 };
 
@@ -70,7 +71,9 @@ attn_mma_kernel(const __grid_constant__ MmaArgs a) {
   float o[NB][4];
 #pragma unroll
   for (int i = 0; i < NB; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
-  const float c2 = a.scale_log2;
+  // rows with a key bias work on t = s * scale_log2 + bias * log2(e) from the start (so the running max sees the bias)
+  const float* bias = (a.key_bias != nullptr && a.rows.bias[b] >= 0) ? a.key_bias + (int64_t)a.rows.bias[b] * a.Nk : nullptr;
+  const float c2 = bias ? 1.f : a.scale_log2;
   const int grow0 = qt * kBM + warp * 16 + g;  // rows grow0 and grow0 + 8
 
 #pragma unroll 1
@@ -106,6 +109,20 @@ attn_mma_kernel(const __grid_constant__ MmaArgs a) {
         }
       }
       const int vc = min(kBN, a.Nk - jj * kBN);
+      if (bias) {
+        // "masked" keys carry finfo.min in the reference; clamped so the product with log2(e) stays finite and a row whose
+        // keys are all masked still comes out as the uniform average, as it does there
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) {
+          const int c = nb * 8 + 2 * t;
+          const float b0 = c < vc ? fmaxf(__ldg(bias + jj * kBN + c) * kLog2e, -3.0e38f) : 0.f;
+          const float b1 = c + 1 < vc ? fmaxf(__ldg(bias + jj * kBN + c + 1) * kLog2e, -3.0e38f) : 0.f;
+          s[nb][0] = fmaf(s[nb][0], a.scale_log2, b0);
+          s[nb][1] = fmaf(s[nb][1], a.scale_log2, b1);
+          s[nb][2] = fmaf(s[nb][2], a.scale_log2, b0);
+          s[nb][3] = fmaf(s[nb][3], a.scale_log2, b1);
+        }
+      }
       if (vc < kBN) {
 #pragma unroll
         for (int nb = 0; nb < 8; ++nb) {
@@ -254,6 +271,7 @@ int ief_attn_mma_launch(const ief_attn_params* p, const IefRowTable& rows, cudaS
   a.scale_log2 = p->scale * kLog2e;
   a.probs = p->probs_out;
   a.probs_accum = p->probs_accum;
+  a.key_bias = p->key_bias;
   a.rows = rows;
   dim3 grid(ief_ceil_div(p->Nq, kBM), p->H, p->B);
   if (p->probs_out) {

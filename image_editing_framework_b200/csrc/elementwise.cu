@@ -2,6 +2,7 @@
 //   ief_cfg_ddim_step     CFG combine + DDIM (reverse) update   p2p/model/sd_utils.py:75-76, inversion/ddim.py:9-18
 //   ief_store_accumulate  AttentionStore.between_steps "+="      p2p/model/attention_base.py:76-82
 //   ief_local_blend       LocalBlend.__call__                    p2p/model/ptp_utils.py:20-32
+//   ief_mask_blend        fg/bg output blend of masked MasaCtrl  masactrl/model/attention_control.py:176-177, 318-319
 #include "ief_common.cuh"
 #include <math.h>
 
@@ -203,7 +204,62 @@ lb_apply_kernel(const __grid_constant__ LbApply a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------ fg/bg blend
+struct BlendRows { uint8_t on[IEF_MAX_ROWS]; };
+
+// fg = fg * w[n] + bg * (1 - w[n]) over [B, N, C]; a thread owns 8 (16-bit) or 4 (fp32) consecutive channels: 16-byte accesses.
+// The three products/sums are rounded separately in fp32, as torch evaluates `fg * mask + bg * (1 - mask)`.
+template <typename T>
+__global__ void __launch_bounds__(256) mask_blend_kernel(T* fg, const T* bg, const float* w, int64_t N, int64_t C, int64_t vec_per_row,
+                                                         int64_t total, BlendRows rows) {
+  constexpr int V = 16 / sizeof(T);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / vec_per_row;  // b * N + n
+    const int64_t b = row / N, n = row - b * N;
+    if (!rows.on[b]) continue;
+    const float wn = __ldg(w + n), wb = __fsub_rn(1.f, wn);
+    const int64_t off = row * C + (i - row * vec_per_row) * V;
+    uint4 f4 = *reinterpret_cast<const uint4*>(fg + off);
+    const uint4 b4 = __ldg(reinterpret_cast<const uint4*>(bg + off));
+    T* fe = reinterpret_cast<T*>(&f4);
+    const T* be = reinterpret_cast<const T*>(&b4);
+#pragma unroll
+    for (int e = 0; e < V; ++e) fe[e] = from_f<T>(__fadd_rn(__fmul_rn(to_f<T>(fe[e]), wn), __fmul_rn(to_f<T>(be[e]), wb)));
+    *reinterpret_cast<uint4*>(fg + off) = f4;
+  }
+}
+
+template <typename T>
+int launch_blend(void* fg, const void* bg, const float* w, int32_t B, int64_t N, int64_t C, const BlendRows& rows, cudaStream_t st) {
+  constexpr int V = 16 / sizeof(T);
+  const int64_t vec_per_row = C / V, total = (int64_t)B * N * vec_per_row;
+  const int64_t blocks = (total + 255) / 256;
+  const int grid = (int)(blocks < 148 * 8 ? blocks : 148 * 8);
+  mask_blend_kernel<T><<<grid, 256, 0, st>>>(static_cast<T*>(fg), static_cast<const T*>(bg), w, N, C, vec_per_row, total, rows);
+  IEF_LAUNCH_OK("mask_blend_kernel");
+  return IEF_OK;
+}
+
 }  // namespace
+
+extern "C" int ief_mask_blend(void* fg, const void* bg, const float* w, int32_t dtype, int32_t B, int64_t N, int64_t C,
+                              const uint8_t* row_mask, void* stream) {
+  IEF_REQUIRE(fg && bg && w, IEF_ERR_INVALID, "ief_mask_blend: null pointer");
+  IEF_REQUIRE(B >= 1 && B <= IEF_MAX_ROWS && N >= 1 && C >= 1, IEF_ERR_INVALID, "ief_mask_blend: bad shape B=%d N=%lld C=%lld", B, (long long)N,
+              (long long)C);
+  const int V = dtype == IEF_F32 ? 4 : 8;
+  IEF_REQUIRE(C % V == 0, IEF_ERR_UNSUPPORTED, "ief_mask_blend: C=%lld must be a multiple of %d", (long long)C, V);
+  IEF_REQUIRE(((reinterpret_cast<uintptr_t>(fg) | reinterpret_cast<uintptr_t>(bg)) & 15) == 0, IEF_ERR_INVALID, "ief_mask_blend: pointers must be 16-byte aligned");
+  BlendRows rows;
+  for (int i = 0; i < IEF_MAX_ROWS; ++i) rows.on[i] = i < B ? (row_mask ? row_mask[i] : 1) : 0;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (dtype) {
+    case IEF_F32: return launch_blend<float>(fg, bg, w, B, N, C, rows, st);
+    case IEF_BF16: return launch_blend<__nv_bfloat16>(fg, bg, w, B, N, C, rows, st);
+    case IEF_F16: return launch_blend<__half>(fg, bg, w, B, N, C, rows, st);
+    default: ief_set_error("ief_mask_blend: unknown dtype %d", dtype); return IEF_ERR_UNSUPPORTED;
+  }
+}
 
 extern "C" int ief_cfg_ddim_step(const void* eps_uncond, const void* eps_cond, const void* x, void* x_out, int64_t n, int32_t dtype,
                                  float guidance, float alpha_t, float alpha_prev, void* stream) {

@@ -74,6 +74,7 @@ struct IefRowTable {
   int32_t k2[IEF_MAX_ROWS];
   int32_t v2[IEF_MAX_ROWS];
   int32_t pslot[IEF_MAX_ROWS];
+  int32_t bias[IEF_MAX_ROWS];  // key_bias vector of the row, -1 = none
   uint8_t active[IEF_MAX_ROWS];
 };
 

@@ -52,12 +52,14 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, sca
               k_src2: Optional[Sequence[int]] = None, v_src2: Optional[Sequence[int]] = None,
               impl: int = IEF_IMPL_AUTO, probs_out: Optional[torch.Tensor] = None, probs_accum: bool = False,
               probs_slot: Optional[Sequence[int]] = None, rows: Optional[Sequence[int]] = None,
+              key_bias: Optional[torch.Tensor] = None, bias_sel: Optional[Sequence[int]] = None,
               out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """O[b] = softmax(scale * Q[q_src[b]] K[k_src[b]]^T) V[v_src[b]]  (ief_attn_fwd).
+    """O[b] = softmax(scale * Q[q_src[b]] K[k_src[b]]^T + key_bias[bias_sel[b]]) V[v_src[b]]  (ief_attn_fwd).
 
     q: [B, Nq, H*d], k/v: [B, Nk, H*d], bf16 or fp16. Returns [B, Nq, H*d] in the same dtype.
+    key_bias: fp32 [n_bias, Nk] per-key additive bias (masked MasaCtrl); bias_sel[b] < 0 leaves row b unbiased.
     """
-    _require_cuda(q, k, v, probs_out, out)
+    _require_cuda(q, k, v, probs_out, out, key_bias)
     if q.dtype not in (torch.bfloat16, torch.float16) or k.dtype != q.dtype or v.dtype != q.dtype:
         raise TypeError(f"attention needs matching bf16/fp16 q,k,v; got {q.dtype}, {k.dtype}, {v.dtype}")
     q4, k4, v4 = _as4(q, heads), _as4(k, heads), _as4(v, heads)
@@ -73,7 +75,14 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, sca
     p.B, p.H, p.Nq, p.Nk, p.d = B, heads, Nq, Nk, d
     p.scale = float(scale)
     p.impl = int(impl)
-    keep = [_cabi.i32_array(x) for x in (q_src, k_src, v_src, k_src2, v_src2, probs_slot)]
+    keep = [_cabi.i32_array(x) for x in (q_src, k_src, v_src, k_src2, v_src2, probs_slot, bias_sel)]
+    if (key_bias is None) != (bias_sel is None):
+        raise ValueError("key_bias and bias_sel go together")
+    if key_bias is not None:
+        if key_bias.dtype != torch.float32 or not key_bias.is_contiguous() or key_bias.dim() != 2 or key_bias.shape[1] != Nk:
+            raise TypeError(f"key_bias must be a contiguous fp32 [n_bias, Nk={Nk}] tensor")
+        p.key_bias, p.n_bias = key_bias.data_ptr(), key_bias.shape[0]
+        p.bias_sel = C.cast(keep[6], C.POINTER(C.c_int32))
     for x in keep:
         if x is not None and len(x) != B:
             raise ValueError("per-row index arrays must have one entry per batch row")
@@ -82,7 +91,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, sca
         row_mask = (C.c_uint8 * B)(*[1 if i in set(rows) else 0 for i in range(B)])
         p.row_mask = C.cast(row_mask, C.POINTER(C.c_uint8))
     p.q_src, p.k_src, p.v_src, p.k_src2, p.v_src2, p.probs_slot = [
-        C.cast(x, C.POINTER(C.c_int32)) if x is not None else None for x in keep]
+        C.cast(x, C.POINTER(C.c_int32)) if x is not None else None for x in keep[:6]]
     if probs_out is not None:
         if probs_out.dtype != torch.float32 or not probs_out.is_contiguous():
             raise TypeError("probs_out must be a contiguous fp32 tensor")
@@ -91,6 +100,25 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, sca
     with torch.cuda.device(q.device):
         _cabi.check("ief_attn_fwd", _cabi.lib().ief_attn_fwd(C.byref(p), _stream()))
     return out
+
+
+def mask_blend(fg: torch.Tensor, bg: torch.Tensor, w: torch.Tensor, rows: Optional[Sequence[int]] = None) -> torch.Tensor:
+    """In place fg[b, n, :] = fg[b, n, :] * w[n] + bg[b, n, :] * (1 - w[n]) for the batch rows in `rows` (ief_mask_blend)."""
+    _require_cuda(fg, bg, w)
+    if fg.dtype not in _DTYPES or bg.dtype != fg.dtype or fg.shape != bg.shape or fg.dim() != 3:
+        raise TypeError(f"mask_blend needs two [B, N, C] tensors of one dtype, got {tuple(fg.shape)} {fg.dtype} / {tuple(bg.shape)} {bg.dtype}")
+    if not fg.is_contiguous() or not bg.is_contiguous():
+        raise TypeError("mask_blend needs contiguous tensors")
+    B, N, Cc = fg.shape
+    if w.dtype != torch.float32 or not w.is_contiguous() or w.numel() != N:
+        raise TypeError(f"w must be a contiguous fp32 vector of {N} weights")
+    row_mask = None
+    if rows is not None:
+        row_mask = (C.c_uint8 * B)(*[1 if i in set(rows) else 0 for i in range(B)])
+    with torch.cuda.device(fg.device):
+        _cabi.check("ief_mask_blend", _cabi.lib().ief_mask_blend(fg.data_ptr(), bg.data_ptr(), w.data_ptr(), _DTYPES[fg.dtype], B, N, Cc,
+                                                                 C.cast(row_mask, C.POINTER(C.c_uint8)) if row_mask is not None else None, _stream()))
+    return fg
 
 
 class CrossEdit:

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define IEF_ABI_VERSION 2
+#define IEF_ABI_VERSION 3
 #define IEF_MAX_ROWS 64  /* max UNet batch rows per call (reference uses 1, 2 or 4) */
 #define IEF_MAX_WORDS 77 /* CLIP context length, p2p/model/ptp_utils.py:8 MAX_NUM_WORDS */
 
@@ -87,6 +87,12 @@ typedef struct ief_attn_params {
   int32_t probs_accum;
   const int32_t* probs_slot; /* HOST [B] or NULL (= b): row b's maps go to probs_out[probs_slot[b]]; <0 = not stored */
   const uint8_t* row_mask; /* HOST [B] or NULL: rows with 0 are skipped (output untouched) */
+  const float* key_bias;   /* device fp32 [n_bias, Nk] or NULL: additive per-key bias on the scaled scores,
+                              softmax(scale*QK^T + key_bias[bias_sel[b]]) — the fore-/background key masks of
+                              MutualSelfAttentionControlMask / MaskAuto (masactrl/model/attention_control.py:139-147,
+                              238-246; "masked" keys carry finfo.min, as there). mma kernel only; no second K/V block. */
+  const int32_t* bias_sel; /* HOST [B] or NULL (= no bias): row b uses key_bias[bias_sel[b]]; <0 = no bias for that row */
+  int32_t n_bias;
 } ief_attn_params;
 
 int ief_attn_fwd(const ief_attn_params* p, void* stream);
@@ -179,6 +185,16 @@ int ief_local_blend(const ief_local_blend_params* p, void* stream);
  */
 int ief_cfg_ddim_step(const void* eps_uncond, const void* eps_cond, const void* x, void* x_out, int64_t n, int32_t dtype,
                       float guidance, float alpha_t, float alpha_prev, void* stream);
+
+/*
+ * ief_mask_blend — spatial fore-/background blend of two attention outputs
+ * (masactrl/model/attention_control.py:176-177, 318-319):
+ *     fg[b,n,:] = fg[b,n,:] * w[n] + bg[b,n,:] * (1 - w[n])      for rows b with row_mask[b] != 0
+ * fg (in/out) and bg: contiguous [B, N, C] of `dtype` (IEF_BF16 / IEF_F16 / IEF_F32); w: device fp32 [N];
+ * row_mask: HOST [B] or NULL (= all rows). Arithmetic in fp32, one rounding on the store.
+ */
+int ief_mask_blend(void* fg, const void* bg, const float* w, int32_t dtype, int32_t B, int64_t N, int64_t C,
+                   const uint8_t* row_mask, void* stream);
 
 /*
  * ief_umma_probe — diagnostic: one CTA runs TMA -> smem -> tcgen05.mma -> TMEM -> global with

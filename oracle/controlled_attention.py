@@ -23,11 +23,16 @@ def batch_to_head(t: torch.Tensor, heads: int) -> torch.Tensor:
     return t.reshape(bh // heads, heads, n, d).permute(0, 2, 1, 3).reshape(bh // heads, n, heads * d)
 
 
-def attention_probs(q: torch.Tensor, k: torch.Tensor, heads: int, scale: float) -> torch.Tensor:
+def attention_probs(q: torch.Tensor, k: torch.Tensor, heads: int, scale: float, key_bias=None) -> torch.Tensor:
     """softmax(scale * Q K^T) as [B*H, N, M] fp32 (diffusers get_attention_scores, called at p2p/model/register.py:47;
-    the same einsum->softmax is spelled out at masactrl/model/register.py:35-44 and pnp/model/register.py:65-75)."""
+    the same einsum->softmax is spelled out at masactrl/model/register.py:35-44 and pnp/model/register.py:65-75).
+    key_bias [B, M]: added to the scaled scores before the softmax, the way the masked MasaCtrl variants add their
+    fore-/background key masks (masactrl/model/attention_control.py:139-147, 238-246)."""
     qh, kh = head_to_batch(q.float(), heads), head_to_batch(k.float(), heads)
-    return (torch.bmm(qh, kh.transpose(1, 2)) * scale).softmax(dim=-1)
+    sim = torch.bmm(qh, kh.transpose(1, 2)) * scale
+    if key_bias is not None:
+        sim = sim + key_bias.float().repeat_interleave(heads, 0)[:, None, :]
+    return sim.softmax(dim=-1)
 
 
 def apply_probs(p: torch.Tensor, v: torch.Tensor, heads: int) -> torch.Tensor:

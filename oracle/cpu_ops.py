@@ -21,14 +21,17 @@ def _as3(t, heads):
 
 
 def attention(q, k, v, heads, scale, *, q_src=None, k_src=None, v_src=None, k_src2=None, v_src2=None, impl=0, probs_out=None,
-              probs_accum=False, probs_slot=None, rows=None, out=None):
+              probs_accum=False, probs_slot=None, rows=None, key_bias=None, bias_sel=None, out=None):
     q, k, v = _as3(q, heads), _as3(k, heads), _as3(v, heads)
     B = q.shape[0]
     ident = list(range(B))
     qq, kk, vv = q[list(q_src or ident)], k[list(k_src or ident)], v[list(v_src or ident)]
     if k_src2 is not None:
         kk, vv = torch.cat([kk, k[list(k_src2)]], 1), torch.cat([vv, v[list(v_src2)]], 1)
-    p = orc.attention_probs(qq, kk, heads, scale)
+    bias = None
+    if key_bias is not None:
+        bias = torch.stack([key_bias[s] if s >= 0 else torch.zeros_like(key_bias[0]) for s in bias_sel])
+    p = orc.attention_probs(qq, kk, heads, scale, key_bias=bias)
     o = orc.apply_probs(p, vv, heads).to(q.dtype)
     if probs_out is not None:
         p4 = p.reshape(B, heads, *p.shape[1:])
@@ -80,6 +83,13 @@ def cross_attention_edit(q, k, v, heads, scale, *, edit=None, step_alpha=None, b
     return o
 
 
+def mask_blend(fg, bg, w, rows=None):
+    sel = list(range(fg.shape[0])) if rows is None else list(rows)
+    wf = w.float().reshape(1, -1, 1)
+    fg[sel] = (fg[sel].float() * wf + bg[sel].float() * (1 - wf)).to(fg.dtype)
+    return fg
+
+
 def store_accumulate(dst, src):
     for d, s in zip(dst, src):
         d += s
@@ -99,7 +109,7 @@ def cfg_ddim_step(eps_uncond, eps_cond, x, guidance, alpha_t, alpha_prev, out=No
     return orc.ddim_step(eps, x, torch.tensor(alpha_t, dtype=torch.float32), torch.tensor(alpha_prev, dtype=torch.float32)).to(x.dtype)
 
 
-_NAMES = ("attention", "cross_attention_edit", "store_accumulate", "local_blend", "cfg_ddim_step")
+_NAMES = ("attention", "cross_attention_edit", "mask_blend", "store_accumulate", "local_blend", "cfg_ddim_step")
 
 
 def install(monkeypatch):

@@ -214,6 +214,52 @@ def gen_masactrl():
                               layer_outputs=rec.records, latents_per_step=per_step, num_att_layers=ctrl.num_att_layers, latent_hw=LAT))
 
 
+def _masa_loop(pipe, ctrl, prompts, latent_seed, hw):
+    context = _context(pipe, prompts)
+    init = _latent(latent_seed, (1, 4, hw, hw))
+    latents = torch.cat([init, init])
+    per_step = []
+    with torch.no_grad():
+        for t in pipe.scheduler.timesteps:
+            noise = pipe.unet(torch.cat([latents] * 2), t, encoder_hidden_states=context).sample
+            nu, nc = noise.chunk(2, dim=0)
+            latents = pipe.scheduler.step(nu + 7.5 * (nc - nu), t, latents, return_dict=True)["prev_sample"]
+            per_step.append(latents.clone())
+    return per_step
+
+
+def gen_masactrl_masks():
+    """MutualSelfAttentionControlMask / MaskAuto (masactrl/model/attention_control.py:110-326) through the reference's own register
+    closure, on a 32x32-latent stand-in (so 16x16 cross-attention layers exist for MaskAuto)."""
+    ref = load_reference("masactrl")
+    cfg = UNetConfig(sample_size=32, block_out_channels=(16, 32, 32, 32), num_heads=(2, 2, 2, 2), cross_attention_dim=32, norm_num_groups=8, name="tiny32")
+    steps, hw = 3, 32
+    prompts = ["a photo of a sitting cat", "a photo of a running cat"]
+    mask_s = torch.zeros(64, 64)
+    mask_s[10:44, 16:50] = 1
+    mask_t = torch.zeros(64, 64)
+    mask_t[20:60, 8:40] = 1
+    out = dict(prompts=prompts, steps=steps, latent_seed=9, pipe_seed=4, guidance=7.5, start_step=1, start_layer=10, latent_hw=hw,
+               config=dataclasses.asdict(cfg), mask_s=mask_s, mask_t=mask_t, thres=0.1, ref_token_idx=[5], cur_token_idx=[5])
+    for name in ("mask", "mask_auto"):
+        pipe = make_pipeline(cfg, seed=4)
+        ref.sd_utils.MasaCtrl(pipe, steps)  # sets the timesteps the reference way
+        if name == "mask":
+            ctrl = ref.attention_control.MutualSelfAttentionControlMask(1, 10, total_steps=steps, mask_s=mask_s, mask_t=mask_t)
+        else:
+            ctrl = ref.attention_control.MutualSelfAttentionControlMaskAuto(1, 10, total_steps=steps, thres=0.1, ref_token_idx=[5], cur_token_idx=[5])
+        ref.register.regiter_attention_editor_diffusers(pipe, ctrl)
+        out[name] = _masa_loop(pipe, ctrl, prompts, 9, hw)
+    # plain mutual control on the same inputs: shows how far the masks move the result (a test that passes with the masks
+    # ignored would be worthless)
+    pipe = make_pipeline(cfg, seed=4)
+    ref.sd_utils.MasaCtrl(pipe, steps)
+    ctrl = ref.attention_control.MutualSelfAttentionControl(1, 10, total_steps=steps)
+    ref.register.regiter_attention_editor_diffusers(pipe, ctrl)
+    out["mutual"] = _masa_loop(pipe, ctrl, prompts, 9, hw)
+    _save("masactrl_masks.pt", out)
+
+
 def gen_pnp():
     ref = load_reference("pnp")
     pipe = make_pipeline(tiny_config(), seed=2)
@@ -371,6 +417,6 @@ def gen_ddim():
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["aligner", "oracle_pins", "ddim", "p2p", "masactrl", "pnp", "pnp_xl", "pix2pix_zero", "p2p_localblend"]
+    which = sys.argv[1:] or ["aligner", "oracle_pins", "ddim", "p2p", "masactrl", "pnp", "pnp_xl", "pix2pix_zero", "p2p_localblend", "masactrl_masks"]
     for w in which:
         globals()["gen_" + w]()

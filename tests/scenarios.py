@@ -97,6 +97,33 @@ def run_masactrl(g, device):
     return ctrl, rec.records, per_step
 
 
+def run_masactrl_masks(g, device, which):
+    """which: 'mask' | 'mask_auto' | 'mutual' — the masked MasaCtrl variants on the 32x32-latent stand-in of masactrl_masks.pt."""
+    pipe = make_pipeline(UNetConfig(**g["config"]), seed=g["pipe_seed"], device=device)
+    steps = g["steps"]
+    pipe.scheduler.set_timesteps(steps)
+    if which == "mask":
+        ctrl = masactrl.MutualSelfAttentionControlMask(g["start_step"], g["start_layer"], total_steps=steps, mask_s=g["mask_s"], mask_t=g["mask_t"])
+    elif which == "mask_auto":
+        ctrl = masactrl.MutualSelfAttentionControlMaskAuto(g["start_step"], g["start_layer"], total_steps=steps, thres=g["thres"],
+                                                          ref_token_idx=g["ref_token_idx"], cur_token_idx=g["cur_token_idx"])
+    else:
+        ctrl = masactrl.MutualSelfAttentionControl(g["start_step"], g["start_layer"], total_steps=steps)
+    masactrl.regiter_attention_editor_diffusers(pipe, ctrl)
+    context = editing.encode_prompts(pipe, g["prompts"])
+    hw = g["latent_hw"]
+    init = latent(g["latent_seed"], (1, 4, hw, hw), device)
+    latents = torch.cat([init, init])
+    fused = FusedDDIM(pipe.scheduler)
+    per_step = []
+    with torch.no_grad():
+        for t in pipe.scheduler.timesteps.tolist():
+            noise = pipe.unet(torch.cat([latents] * 2), t, encoder_hidden_states=context).sample
+            latents = fused.step(noise, t, latents, g["guidance"])
+            per_step.append(latents.float().cpu())
+    return ctrl, per_step
+
+
 def run_pnp(g, device, xl=False):
     pipe = make_pipeline(UNetConfig(**g["config"]) if xl else tiny_config(), seed=g["pipe_seed"], device=device)
     steps = g["steps"]

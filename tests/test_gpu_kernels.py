@@ -146,6 +146,54 @@ def test_attn_probs_out(cuda, shape):
     assert (probs.cpu() - 2 * want_p[lo * H:]).abs().max().item() < 1e-2
 
 
+@pytest.mark.parametrize("shape", [(4, 2, 256, 256, 40), (4, 2, 1024, 1024, 80), (4, 2, 100, 100, 64), (4, 8, 4096, 4096, 40)])
+def test_attn_key_bias_masked_masactrl(cuda, shape):
+    """softmax(scale QK^T + key_bias[bias_sel[b]]): fore-/background key masks of the masked MasaCtrl variants, including a
+    row set whose keys are ALL masked (the reference then degenerates to the uniform average — finfo.min absorbs the scores)."""
+    B, H, N, M, d = shape
+    q, k, v = _qkv(B, N, M, H, d, 21)
+    g = torch.Generator().manual_seed(3)
+    m = (torch.rand(M, generator=g) > 0.6).float()
+    fmin = torch.finfo(torch.float32).min
+    bias = torch.stack([m.masked_fill(m == 0, fmin), m.masked_fill(m == 1, fmin), torch.full((M,), fmin), 0.5 * torch.randn(M, generator=g)])
+    sel = [-1, 0, 2, 1] if N <= 256 else [3, 0, -1, 1]
+    src = [0, 0, 2, 2]
+    scale = d ** -0.5
+    full = torch.stack([bias[s_] if s_ >= 0 else torch.zeros(M) for s_ in sel])
+    p = orc.attention_probs(q, k[src], H, scale, key_bias=full)
+    want = orc.apply_probs(p, v[src], H)
+    got = ops.attention(q.to(cuda), k.to(cuda), v.to(cuda), H, scale, k_src=src, v_src=src, key_bias=bias.to(cuda), bias_sel=sel)
+    torch.cuda.synchronize()
+    assert _cabi.last_attn_impl() == "mma"
+    err = (got.float().cpu() - want).abs().max().item()
+    assert err < TOL, f"max abs err {err}"
+    if 2 in sel:  # all keys masked -> uniform average of V
+        b = sel.index(2)
+        assert (got[b].float().cpu() - v[src[b]].float().mean(0, keepdim=True)).abs().max().item() < TOL
+    with pytest.raises(_cabi.IefError):
+        ops.attention(q.to(cuda), k.to(cuda), v.to(cuda), H, scale, key_bias=bias.to(cuda), bias_sel=sel, impl=ops.IEF_IMPL_TCGEN05)
+    with pytest.raises(_cabi.IefError):
+        ops.attention(q.to(cuda), k.to(cuda), v.to(cuda), H, scale, key_bias=bias.to(cuda), bias_sel=[0, 1, 2, 7])
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+def test_mask_blend(cuda, dtype):
+    g = torch.Generator().manual_seed(4)
+    B, N, Cc = 4, 1024, 320
+    fg, bg = torch.randn(B, N, Cc, generator=g).to(dtype), torch.randn(B, N, Cc, generator=g).to(dtype)
+    w = torch.rand(N, generator=g)
+    w[::3] = 1.0
+    w[1::3] = 0.0
+    want = fg.clone()
+    wf = w.reshape(1, N, 1)
+    want[[1, 3]] = (fg[[1, 3]].float() * wf + bg[[1, 3]].float() * (1 - wf)).to(dtype)  # reference :176-177 (fp32 there)
+    got = ops.mask_blend(fg.to(cuda), bg.to(cuda), w.to(cuda), rows=[1, 3])
+    torch.cuda.synchronize()
+    assert torch.equal(got.cpu(), want), "mask blend must be bit-exact (three separately rounded fp32 ops, one final rounding)"
+    with pytest.raises(TypeError):
+        ops.mask_blend(fg.to(cuda), bg.to(cuda)[:, :, :8], w.to(cuda))
+
+
 def test_attn_rejects_bad_arguments(cuda):
     q, k, v = _qkv(2, 64, 64, 2, 36, 0)  # head_dim 36 is not a multiple of 8
     with pytest.raises(_cabi.IefError):

@@ -36,7 +36,7 @@ def test_struct_sizes_match_header_layout():
     import ctypes as C
     # 4 tensor4 (32 B each) + 6 int32 + float + int32 (=160) + 5 pointers + ptr + int32(+pad) + 2 pointers
     assert C.sizeof(_cabi.Tensor4) == 32
-    assert C.sizeof(_cabi.AttnParams) == 128 + 32 + 5 * 8 + 8 + 8 + 8 + 8
+    assert C.sizeof(_cabi.AttnParams) == 128 + 32 + 5 * 8 + 8 + 8 + 8 + 8 + 8 + 8 + 8
     assert C.sizeof(_cabi.CrossParams) == 128 + 32 + 8 + 8 + 8 + 7 * 8 + 8 + 8 + 8
 
 
@@ -265,6 +265,19 @@ def test_masactrl_host_logic_reproduces_reference(monkeypatch):
     ctrl, records, per_step = scenarios.run_masactrl(g, torch.device("cpu"))
     assert ctrl.num_att_layers == g["num_att_layers"] == 32
     _compare(records, per_step, g)
+
+
+@pytest.mark.parametrize("which", ["mask", "mask_auto"])
+def test_masactrl_masked_variants_reproduce_reference(monkeypatch, which):
+    """MutualSelfAttentionControlMask / MaskAuto: key-bias tables, fg/bg passes, spatial blend, 16x16 cross-map aggregation."""
+    cpu_backend.install(monkeypatch)
+    g = golden("masactrl_masks.pt")
+    ctrl, per_step = scenarios.run_masactrl_masks(g, torch.device("cpu"), which)
+    for a, b in zip(per_step, g[which]):
+        assert torch.allclose(a, b, atol=2e-4), (a - b).abs().max()
+    # the masks matter: plain mutual control on the same inputs ends somewhere else
+    assert (g["mutual"][-1] - g[which][-1]).abs().max() > 50 * (per_step[-1] - g[which][-1]).abs().max()
+    assert ctrl.cur_step == g["steps"]
 
 
 def test_pnp_host_logic_reproduces_reference(monkeypatch):
