@@ -12,7 +12,9 @@ from typing import List, Optional
 
 import torch
 
+from . import _cabi
 from .ddim import FusedDDIM
+from .graphs import GraphedUNet
 from .p2p.register import register_attention_control
 from .pnp import register as pnp_register
 
@@ -28,41 +30,55 @@ def encode_prompts(model, prompts: List[str]) -> torch.Tensor:
 
 @torch.no_grad()
 def denoise(model, latents: torch.Tensor, context: torch.Tensor, num_inference_steps: int, guidance_scale: float,
-            step_callback=None, per_step=None) -> torch.Tensor:
+            step_callback=None, per_step=None, graphs: bool = False, controller=None, graph_key_fn=None, stats: Optional[dict] = None) -> torch.Tensor:
+    """The 50-step loop. `graphs=True` replays each control phase of the UNet forward from a CUDA graph (graphs.GraphedUNet):
+    `controller` is the installed controller / editor (its graph_key() names the phase), `graph_key_fn(t)` adds
+    timestep-dependent host state (the PnP schedules)."""
     model.scheduler.set_timesteps(num_inference_steps)
     fused = FusedDDIM(model.scheduler)
-    for t in model.scheduler.timesteps.tolist():
-        if per_step is not None:
-            per_step(t)
-        noise_pred = model.unet(torch.cat([latents] * 2), t, encoder_hidden_states=context)["sample"]
-        latents = fused.step(noise_pred, t, latents, guidance_scale)
-        if step_callback is not None:
-            latents = step_callback(latents)
+    runner = GraphedUNet(model.unet, controller, graph_key_fn, launch_counter=_cabi.launch_count) if graphs else None
+    try:
+        for t in model.scheduler.timesteps.tolist():
+            if per_step is not None:
+                per_step(t)
+            x = torch.cat([latents] * 2)
+            noise_pred = runner(x, t, context) if runner is not None else model.unet(x, t, encoder_hidden_states=context)["sample"]
+            latents = fused.step(noise_pred, t, latents, guidance_scale)
+            if step_callback is not None:
+                latents = step_callback(latents)
+    finally:
+        if runner is not None:
+            if stats is not None:
+                stats.update(replays=runner.replays, captures=runner.captures, eager_calls=runner.eager_calls, replayed_launches=runner.replayed_launches)
+            runner.close()
     return latents
 
 
 @torch.no_grad()
 def p2p_edit(model, prompts: List[str], controller, latent: torch.Tensor, num_inference_steps: int = 50, guidance_scale: float = 7.5,
-             context: Optional[torch.Tensor] = None) -> torch.Tensor:
+             context: Optional[torch.Tensor] = None, graphs: bool = False, stats: Optional[dict] = None) -> torch.Tensor:
     if controller is not None:
         register_attention_control(model, controller)
     context = encode_prompts(model, prompts) if context is None else context
     latents = (latent * model.scheduler.init_noise_sigma).expand(len(prompts), *latent.shape[1:]).contiguous()
     return denoise(model, latents, context, num_inference_steps, guidance_scale,
-                   step_callback=controller.step_callback if controller is not None else None)
+                   step_callback=controller.step_callback if controller is not None else None, graphs=graphs, controller=controller, stats=stats)
 
 
 @torch.no_grad()
 def masactrl_edit(model, prompts: List[str], latents: torch.Tensor, num_inference_steps: int = 50, guidance_scale: float = 7.5,
-                  context: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """The editor must already be registered (masactrl/edit_real.py:137-138)."""
+                  context: Optional[torch.Tensor] = None, graphs: bool = False, editor=None, stats: Optional[dict] = None) -> torch.Tensor:
+    """The editor must already be registered (masactrl/edit_real.py:137-138); pass it as `editor` with graphs=True."""
     context = encode_prompts(model, prompts) if context is None else context
-    return denoise(model, latents, context, num_inference_steps, guidance_scale)
+    if graphs and editor is None:
+        raise ValueError("masactrl_edit(graphs=True) needs the registered editor (its step list decides which graph a step replays)")
+    return denoise(model, latents, context, num_inference_steps, guidance_scale, graphs=graphs, controller=editor, stats=stats)
 
 
 @torch.no_grad()
 def pnp_edit(model, prompts: List[str], latents: torch.Tensor, num_inference_steps: int = 50, guidance_scale: float = 7.5,
-             pnp_attn_t: float = 0.5, pnp_f_t: float = 0.8, context: Optional[torch.Tensor] = None, xl: bool = False) -> torch.Tensor:
+             pnp_attn_t: float = 0.5, pnp_f_t: float = 0.8, context: Optional[torch.Tensor] = None, xl: bool = False,
+             graphs: bool = False, stats: Optional[dict] = None) -> torch.Tensor:
     model.scheduler.set_timesteps(num_inference_steps)
     ts = model.scheduler.timesteps
     qk_t, f_t = int(num_inference_steps * pnp_attn_t), int(num_inference_steps * pnp_f_t)
@@ -78,7 +94,9 @@ def pnp_edit(model, prompts: List[str], latents: torch.Tensor, num_inference_ste
     reg[1](model, conv_sched)
     context = encode_prompts(model, prompts) if context is None else context
     try:
-        return denoise(model, latents, context, num_inference_steps, guidance_scale, per_step=lambda t: reg[2](model, t))
+        qk_set, conv_set = frozenset(int(t) for t in qk_sched), frozenset(int(t) for t in conv_sched)
+        return denoise(model, latents, context, num_inference_steps, guidance_scale, per_step=lambda t: reg[2](model, t), graphs=graphs,
+                       graph_key_fn=lambda t: (t in qk_set or t == 1000, t in conv_set or t == 1000), stats=stats)
     finally:
         reg[3](model)
         reg[4](model)

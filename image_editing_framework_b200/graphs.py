@@ -8,7 +8,7 @@ controller's counters itself on replay.
 """
 from __future__ import annotations
 
-from typing import Callable, Sequence
+from typing import Callable, Dict, Hashable, Optional, Sequence
 
 import torch
 
@@ -39,3 +39,84 @@ class GraphedCall:
         self.graph.replay()
         self.replays += 1
         return self.static_out
+
+
+class GraphedUNet:
+    """Phase-keyed CUDA-graph cache around `unet(x, t, encoder_hidden_states=ctx)` for the 50-step loops.
+
+    Which kernels a forward launches, and with which by-value arguments, depends on host state of the installed controller
+    (is this step inside the self-replace window / the MasaCtrl step list / the PnP injection schedule, does the map store
+    overwrite or accumulate ...). The controller describes that state with three methods (see AttentionControl /
+    masactrl.AttentionBase for the defaults):
+
+        graph_key()      hashable summary of everything host-side that shapes the launches of the NEXT forward;
+                         None = "this controller cannot be replayed" (the call then always runs eagerly)
+        graph_prepare()  refresh the fixed device buffers captured kernels read per step (e.g. the cross-replace alpha row)
+        graph_advance()  what one complete eager forward does to the host counters (cur_step += 1, between_steps() ...)
+
+    For each distinct key the first forward runs eagerly (it is the warm-up, with the real semantics), the second is
+    captured and replayed once (stream capture only records, so the hooks tick the counters exactly as an eager forward
+    does), later ones copy the inputs into the static buffers, replay and call graph_advance().
+    """
+
+    def __init__(self, unet, controller=None, key_fn: Optional[Callable[[int], Hashable]] = None, launch_counter=None):
+        self.unet, self.controller, self.key_fn, self.launch_counter = unet, controller, key_fn, launch_counter
+        self._seen: Dict[Hashable, int] = {}
+        self._graphs: Dict[Hashable, tuple] = {}
+        self._t: Dict[int, torch.Tensor] = {}
+        self.replays = self.eager_calls = self.captures = self.replayed_launches = 0
+        if controller is not None:
+            controller._graph_mode = True
+
+    def _tstep(self, t, device) -> torch.Tensor:
+        if torch.is_tensor(t):
+            return t
+        if t not in self._t:
+            self._t[t] = torch.tensor(t, dtype=torch.int64, device=device)
+        return self._t[t]
+
+    def close(self):
+        if self.controller is not None:
+            self.controller._graph_mode = False
+        self._graphs.clear()
+
+    def __call__(self, x: torch.Tensor, t, ctx: torch.Tensor) -> torch.Tensor:
+        c = self.controller
+        ckey = c.graph_key() if c is not None else ()
+        if c is not None:
+            c.graph_prepare()
+        t_host = int(t) if not torch.is_tensor(t) else None
+        if ckey is None:
+            self.eager_calls += 1
+            return self.unet(x, t, encoder_hidden_states=ctx)["sample"]
+        key = (tuple(x.shape), x.dtype, tuple(ctx.shape), ckey, self.key_fn(t_host) if self.key_fn is not None else ())
+        n = self._seen.get(key, 0)
+        self._seen[key] = n + 1
+        td = self._tstep(t, x.device)
+        if n == 0:
+            self.eager_calls += 1
+            return self.unet(x, td, encoder_hidden_states=ctx)["sample"]
+        if n == 1:
+            xs, ts, cs = x.clone(), td.clone(), ctx.clone()
+            graph = torch.cuda.CUDAGraph()
+            before = self.launch_counter() if self.launch_counter else 0
+            with torch.cuda.graph(graph), torch.no_grad():
+                out = self.unet(xs, ts, encoder_hidden_states=cs)["sample"]
+            launches = (self.launch_counter() - before) if self.launch_counter else 0
+            self._graphs[key] = (graph, xs, ts, cs, out, launches)
+            self.captures += 1
+            graph.replay()
+            self.replays += 1
+            self.replayed_launches += launches
+            return out
+        graph, xs, ts, cs, out, launches = self._graphs[key]
+        xs.copy_(x, non_blocking=True)
+        ts.copy_(td, non_blocking=True)
+        if cs.data_ptr() != ctx.data_ptr():
+            cs.copy_(ctx, non_blocking=True)
+        graph.replay()
+        self.replays += 1
+        self.replayed_launches += launches
+        if c is not None:
+            c.graph_advance()
+        return out

@@ -63,6 +63,20 @@ class AttentionBase(abc.ABC):
         self.cur_step = 0
         self.cur_att_layer = 0
 
+    # ---- CUDA-graph replay protocol (graphs.GraphedUNet) ---------------------------------------------------------
+    _graph_mode = False
+
+    def graph_key(self):
+        return () if self.cur_att_layer == 0 else None
+
+    def graph_prepare(self) -> None:
+        return None
+
+    def graph_advance(self) -> None:
+        self.cur_att_layer = 0
+        self.cur_step += 1
+        self.after_step()
+
 
 class AttentionStore(AttentionBase):
     """masactrl/model/attention_base.py:33-66: keeps every map with N <= 64^2 for steps in (min_step, max_step).
@@ -78,6 +92,9 @@ class AttentionStore(AttentionBase):
         self.cross_attns: List[torch.Tensor] = []
         self.self_attns_step: List[torch.Tensor] = []
         self.cross_attns_step: List[torch.Tensor] = []
+
+    def graph_key(self):
+        return None  # keeps per-step python lists of freshly allocated maps: not replayable
 
     def after_step(self):
         if self.cur_step > self.min_step and self.cur_step < self.max_step:

@@ -37,6 +37,10 @@ class MutualSelfAttentionControl(AttentionBase):
         # reference gate :56 — note the self-attention layer index is cur_att_layer // 2
         return not (is_cross or self.cur_step not in self._steps or self.cur_att_layer // 2 not in self._layers)
 
+    def graph_key(self):
+        base = super().graph_key()
+        return None if base is None else base + (self.cur_step in self._steps,)
+
     def fused_forward(self, q, k, v, is_cross, place_in_unet, num_heads, scale):
         if not self._controlled(is_cross):
             return super().fused_forward(q, k, v, is_cross, place_in_unet, num_heads, scale)
@@ -167,9 +171,14 @@ class MutualSelfAttentionControlMaskAuto(_MaskedMutualMixin, MutualSelfAttention
         attn_map = torch.stack(self.cross_attns, dim=1).mean(1)  # (B, N, dim)
         res = int(np.sqrt(attn_map.shape[-2]))
         attn_map = attn_map.reshape(-1, res, res, attn_map.shape[-1])
-        image = attn_map[..., idx]
         if isinstance(idx, list):
-            image = image.sum(-1)
+            # = attn_map[..., idx].sum(-1); python-int column views instead of a list index, which would build an index
+            # tensor on the host and copy it over (not allowed inside CUDA-graph capture)
+            image = attn_map[..., idx[0]]
+            for i in idx[1:]:
+                image = image + attn_map[..., i]
+        else:
+            image = attn_map[..., idx]
         image_min = image.min(dim=1, keepdim=True)[0].min(dim=2, keepdim=True)[0]
         image_max = image.max(dim=1, keepdim=True)[0].max(dim=2, keepdim=True)[0]
         return (image - image_min) / (image_max - image_min)

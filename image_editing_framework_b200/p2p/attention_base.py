@@ -86,6 +86,24 @@ class AttentionControl(abc.ABC):
         self.cur_step = 0
         self.cur_att_layer = 0
 
+    # ---- CUDA-graph replay protocol (graphs.GraphedUNet) ---------------------------------------------------------
+    _graph_mode = False
+
+    def graph_key(self):
+        """Host state that shapes the launches of the next UNet forward; None = not replayable."""
+        if self.LOW_RESOURCE or self.cur_att_layer != 0:
+            return None  # two UNet passes per step / a forward in flight: run eagerly
+        return ()
+
+    def graph_prepare(self) -> None:
+        return None
+
+    def graph_advance(self) -> None:
+        """Effect of one complete forward on the counters (the num_att_layers `_tick`s of :23-27)."""
+        self.cur_att_layer = 0
+        self.cur_step += 1
+        self.between_steps()
+
 
 def _plain(q, k, v, heads, scale, is_cross):
     if is_cross and k.shape[1] <= 80:
@@ -160,6 +178,13 @@ class AttentionStore(AttentionControl):
     def get_average_attention(self):
         return {key: [item / self.cur_step for item in self.attention_store[key]] for key in self.attention_store}
 
+    def graph_key(self):
+        base = super().graph_key()
+        if base is None:
+            return None
+        # the first stored step allocates + overwrites the store, later ones accumulate into the same buffers
+        return base + (("store", len(self.attention_store) != 0) if self._store_enabled else ("nostore",),)
+
     def reset(self):
         super().reset()
         self.step_store = self.get_empty_store()
@@ -187,6 +212,7 @@ class AttentionControlEdit(AttentionStore, abc.ABC):
         self._device = torch.device(device)
         # [num_steps+1, n_targets, 77] fp32 contiguous: row `cur_step` is handed to the kernel as-is
         self._alpha_table = self.cross_replace_alpha.reshape(num_steps + 1, self.batch_size - 1, -1).to(torch.float32).contiguous()
+        self._alpha_cur = self._alpha_table[0].clone()  # fixed buffer read by captured kernels (graph mode only)
         self._edit: Optional[ops.CrossEdit] = None
 
     @abc.abstractmethod
@@ -213,7 +239,8 @@ class AttentionControlEdit(AttentionStore, abc.ABC):
             if self._edit is None:
                 self._edit = self.cross_edit()
             _, base, slot = self._row_tables(B)
-            kw = dict(edit=self._edit, step_alpha=self._alpha_table[self.cur_step], base_row=base, edit_slot=slot)
+            alpha = self._alpha_cur if self._graph_mode else self._alpha_table[self.cur_step]
+            kw = dict(edit=self._edit, step_alpha=alpha, base_row=base, edit_slot=slot)
             return self._attend_and_store(q, k, v, heads, scale, True, place_in_unet, cross_kw=kw)
         src = None
         if self.num_self_replace[0] <= self.cur_step < self.num_self_replace[1] and N <= _SELF_REPLACE_MAX_TOKENS:
@@ -226,3 +253,13 @@ class AttentionControlEdit(AttentionStore, abc.ABC):
         if self.local_blend is not None:
             x_t = self.local_blend(x_t, self.attention_store)
         return x_t
+
+    def graph_key(self):
+        base = super().graph_key()
+        if base is None or self.cur_step >= self._alpha_table.shape[0]:
+            return None
+        return base + (self.num_self_replace[0] <= self.cur_step < self.num_self_replace[1],)
+
+    def graph_prepare(self) -> None:
+        if self._graph_mode and self.cur_step < self._alpha_table.shape[0]:
+            self._alpha_cur.copy_(self._alpha_table[self.cur_step], non_blocking=True)

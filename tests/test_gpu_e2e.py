@@ -164,3 +164,45 @@ def test_cuda_graph_replay_equals_eager(cuda):
         want2 = fwd(x2, t, ctx).clone()
     assert torch.equal(g(x, t, ctx), want)
     assert torch.equal(g(x2, t, ctx), want2)
+
+
+@pytest.mark.parametrize("method", ["p2p_replace_localblend", "p2p_refine", "masactrl", "masactrl_mask_auto", "pnp"])
+def test_graph_replay_matches_eager(cuda, method):
+    """editing.*(graphs=True): phase-keyed CUDA-graph replay of the UNet forwards gives the eager result, with the controller
+    counters, the map store and LocalBlend behaving as in eager mode."""
+    from image_editing_framework_b200 import p2p, masactrl, editing
+    from image_editing_framework_b200.standin import make_pipeline
+    from image_editing_framework_b200.standin.unet import UNetConfig
+    lb_case = method == "p2p_replace_localblend"   # LocalBlend reads the 16x16 maps of the 64x64-latent topology
+    cfg = UNetConfig(**(golden("p2p_localblend.pt") if lb_case else golden("masactrl_masks.pt"))["config"])
+    hw = 64 if lb_case else 32
+    prompts = ["a photo of a cat sitting on a bench", "a photo of a dog sitting on a bench"]
+    steps = 10
+    results, stats = [], {}
+    for graphs in (False, True):
+        pipe = make_pipeline(cfg, seed=7, device=cuda)
+        lat1 = scenarios.latent(11, (1, 4, hw, hw), cuda)
+        lat2 = torch.cat([lat1, lat1])
+        common = dict(prompts=prompts, tokenizer=pipe.tokenizer, num_steps=steps, cross_replace_steps=0.8, self_replace_steps=0.4, device=cuda)
+        if method.startswith("p2p"):
+            if method == "p2p_refine":
+                ctrl = p2p.AttentionRefine(**common)
+            else:
+                ctrl = p2p.AttentionReplace(local_blend=p2p.LocalBlend(pipe.tokenizer, prompts, [["cat"], ["dog"]], device=cuda), **common)
+            out = editing.p2p_edit(pipe, prompts, ctrl, lat1, steps, 7.5, graphs=graphs, stats=stats)
+            assert ctrl.cur_step == steps and ctrl.cur_att_layer == 0
+            if method == "p2p_replace_localblend":
+                results.append(ctrl.get_average_attention()["up_cross"][0].float().cpu())
+        elif method.startswith("masactrl"):
+            ed = (masactrl.MutualSelfAttentionControl(3, 10, total_steps=steps) if method == "masactrl" else
+                  masactrl.MutualSelfAttentionControlMaskAuto(3, 10, total_steps=steps, ref_token_idx=[5], cur_token_idx=[5]))
+            masactrl.regiter_attention_editor_diffusers(pipe, ed)
+            out = editing.masactrl_edit(pipe, prompts, lat2, steps, 7.5, graphs=graphs, editor=ed, stats=stats)
+            assert ed.cur_step == steps and ed.cur_att_layer == 0
+        else:
+            out = editing.pnp_edit(pipe, prompts, lat2, steps, 7.5, graphs=graphs, stats=stats)
+        results.append(out.float().cpu())
+    n = len(results) // 2
+    for a, b in zip(results[:n], results[n:]):
+        assert psnr(b, a) >= 50.0, f"graph replay deviates from eager: PSNR {psnr(b, a):.1f} dB"
+    assert stats["replays"] >= steps - 6 and stats["captures"] >= 1 and stats["replayed_launches"] > 0, stats

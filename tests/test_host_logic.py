@@ -347,3 +347,45 @@ def test_attention_mask_is_rejected(monkeypatch):
     attn = pipe.unet.mid_block.attentions[0].transformer_blocks[0].attn1
     with pytest.raises(NotImplementedError):
         attn.forward(torch.zeros(1, 4, attn.to_q.in_features), attention_mask=torch.zeros(1, 4))
+
+
+def test_graph_replay_protocol_tracks_eager_counters(monkeypatch):
+    """graph_advance() must leave a controller exactly where a complete eager forward leaves it, and graph_key() must change
+    whenever the host state that shapes the launches changes (self-replace window, first stored step, MasaCtrl step list)."""
+    import copy
+    from image_editing_framework_b200 import p2p, masactrl, editing
+    from image_editing_framework_b200.standin import make_pipeline, tiny_config
+    cpu_backend.install(monkeypatch)
+    dev = torch.device("cpu")
+    pipe = make_pipeline(tiny_config(), seed=1, device=dev)
+    prompts = ["a photo of a cat sitting on a bench", "a photo of a dog sitting on a bench"]
+    steps = 5
+    pipe.scheduler.set_timesteps(steps)
+    ctx = editing.encode_prompts(pipe, prompts)
+    x = torch.randn(4, 4, 8, 8)
+    lb = p2p.LocalBlend(pipe.tokenizer, prompts, [["cat"], ["dog"]], device=dev)
+    ctrl = p2p.AttentionReplace(prompts, pipe.tokenizer, steps, 0.8, 0.6, lb, device=dev)
+    p2p.register_attention_control(pipe, ctrl)
+    keys = []
+    with torch.no_grad():
+        for t in pipe.scheduler.timesteps.tolist():
+            keys.append(ctrl.graph_key())
+            shadow = copy.copy(ctrl)
+            shadow.graph_advance()
+            pipe.unet(x, t, encoder_hidden_states=ctx)
+            assert (ctrl.cur_step, ctrl.cur_att_layer, ctrl._slot) == (shadow.cur_step, shadow.cur_att_layer, shadow._slot)
+    # store: first step allocates, later accumulate; self-replace window = steps [0, 3)
+    assert keys == [(("store", False), True), (("store", True), True), (("store", True), True), (("store", True), False), (("store", True), False)]
+    p2p.unregister_attention_control(pipe, ctrl)
+    ed = masactrl.MutualSelfAttentionControl(2, 10, total_steps=steps)
+    masactrl.regiter_attention_editor_diffusers(pipe, ed)
+    keys = []
+    with torch.no_grad():
+        for t in pipe.scheduler.timesteps.tolist():
+            keys.append(ed.graph_key())
+            shadow = copy.copy(ed)
+            shadow.graph_advance()
+            pipe.unet(x, t, encoder_hidden_states=ctx)
+            assert (ed.cur_step, ed.cur_att_layer) == (shadow.cur_step, shadow.cur_att_layer)
+    assert keys == [(False,), (False,), (True,), (True,), (True,)]
+    assert masactrl.AttentionStore().graph_key() is None

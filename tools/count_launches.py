@@ -11,6 +11,8 @@ from image_editing_framework_b200.editing import encode_prompts
 
 dev = torch.device("cuda:0")
 pipe, cfg = bench.build_pipeline("sd15", dev, torch.bfloat16)
+if "--nchw" not in sys.argv:
+    pipe.unet.to(memory_format=torch.channels_last)  # as bench.py runs it
 ctx = encode_prompts(pipe, bench.PROMPTS)
 with contextlib.redirect_stdout(io.StringIO()):
     ed = masactrl.MutualSelfAttentionControl(4, 10, total_steps=50)
