@@ -8,7 +8,7 @@ Orchestration only — every attention call goes through the registered closures
 """
 from __future__ import annotations
 
-from typing import List, Optional
+from typing import List, Optional, Union
 
 import torch
 
@@ -30,13 +30,21 @@ def encode_prompts(model, prompts: List[str]) -> torch.Tensor:
 
 @torch.no_grad()
 def denoise(model, latents: torch.Tensor, context: torch.Tensor, num_inference_steps: int, guidance_scale: float,
-            step_callback=None, per_step=None, graphs: bool = False, controller=None, graph_key_fn=None, stats: Optional[dict] = None) -> torch.Tensor:
-    """The 50-step loop. `graphs=True` replays each control phase of the UNet forward from a CUDA graph (graphs.GraphedUNet):
-    `controller` is the installed controller / editor (its graph_key() names the phase), `graph_key_fn(t)` adds
-    timestep-dependent host state (the PnP schedules)."""
+            step_callback=None, per_step=None, graphs: Union[bool, GraphedUNet] = False, controller=None, graph_key_fn=None,
+            stats: Optional[dict] = None) -> torch.Tensor:
+    """The 50-step loop. With `graphs` each control phase of the UNet forward is replayed from a CUDA graph
+    (graphs.GraphedUNet): `controller` is the installed controller / editor (its graph_key() names the phase),
+    `graph_key_fn(t)` adds timestep-dependent host state (the PnP schedules). `graphs=True` builds a runner for this call
+    only (captures included); pass a GraphedUNet built once for the same unet + controller to amortise them over edits."""
     model.scheduler.set_timesteps(num_inference_steps)
     fused = FusedDDIM(model.scheduler)
-    runner = GraphedUNet(model.unet, controller, graph_key_fn, launch_counter=_cabi.launch_count) if graphs else None
+    own = graphs is True
+    runner = GraphedUNet(model.unet, controller, graph_key_fn, launch_counter=_cabi.launch_count) if own else (graphs or None)
+    if runner is not None and not own:
+        if runner.controller is not controller:
+            raise ValueError("the GraphedUNet passed as `graphs` was built for a different controller")
+        if runner.key_fn is None:
+            runner.key_fn = graph_key_fn
     try:
         for t in model.scheduler.timesteps.tolist():
             if per_step is not None:
@@ -50,13 +58,14 @@ def denoise(model, latents: torch.Tensor, context: torch.Tensor, num_inference_s
         if runner is not None:
             if stats is not None:
                 stats.update(replays=runner.replays, captures=runner.captures, eager_calls=runner.eager_calls, replayed_launches=runner.replayed_launches)
-            runner.close()
+            if own:
+                runner.close()
     return latents
 
 
 @torch.no_grad()
 def p2p_edit(model, prompts: List[str], controller, latent: torch.Tensor, num_inference_steps: int = 50, guidance_scale: float = 7.5,
-             context: Optional[torch.Tensor] = None, graphs: bool = False, stats: Optional[dict] = None) -> torch.Tensor:
+             context: Optional[torch.Tensor] = None, graphs: Union[bool, GraphedUNet] = False, stats: Optional[dict] = None) -> torch.Tensor:
     if controller is not None:
         register_attention_control(model, controller)
     context = encode_prompts(model, prompts) if context is None else context
@@ -67,7 +76,8 @@ def p2p_edit(model, prompts: List[str], controller, latent: torch.Tensor, num_in
 
 @torch.no_grad()
 def masactrl_edit(model, prompts: List[str], latents: torch.Tensor, num_inference_steps: int = 50, guidance_scale: float = 7.5,
-                  context: Optional[torch.Tensor] = None, graphs: bool = False, editor=None, stats: Optional[dict] = None) -> torch.Tensor:
+                  context: Optional[torch.Tensor] = None, graphs: Union[bool, GraphedUNet] = False, editor=None,
+                  stats: Optional[dict] = None) -> torch.Tensor:
     """The editor must already be registered (masactrl/edit_real.py:137-138); pass it as `editor` with graphs=True."""
     context = encode_prompts(model, prompts) if context is None else context
     if graphs and editor is None:
@@ -78,7 +88,7 @@ def masactrl_edit(model, prompts: List[str], latents: torch.Tensor, num_inferenc
 @torch.no_grad()
 def pnp_edit(model, prompts: List[str], latents: torch.Tensor, num_inference_steps: int = 50, guidance_scale: float = 7.5,
              pnp_attn_t: float = 0.5, pnp_f_t: float = 0.8, context: Optional[torch.Tensor] = None, xl: bool = False,
-             graphs: bool = False, stats: Optional[dict] = None) -> torch.Tensor:
+             graphs: Union[bool, GraphedUNet] = False, stats: Optional[dict] = None) -> torch.Tensor:
     model.scheduler.set_timesteps(num_inference_steps)
     ts = model.scheduler.timesteps
     qk_t, f_t = int(num_inference_steps * pnp_attn_t), int(num_inference_steps * pnp_f_t)

@@ -57,6 +57,11 @@ class GraphedUNet:
     For each distinct key the first forward runs eagerly (it is the warm-up, with the real semantics), the second is
     captured and replayed once (stream capture only records, so the hooks tick the counters exactly as an eager forward
     does), later ones copy the inputs into the static buffers, replay and call graph_advance().
+
+    Capturing a ~1100-kernel forward costs a few hundred ms, so a runner pays off when it outlives one edit: build it once
+    for a (unet, controller) pair, pass it as `graphs=runner` to the drivers in editing.py and `controller.reset()` between
+    images — the captured pointers (map-store buffers, alpha row, mapper tables) belong to the controller and stay valid for
+    its lifetime. MasaCtrl / PnP graphs do not depend on the prompts (the context is a copied input).
     """
 
     def __init__(self, unet, controller=None, key_fn: Optional[Callable[[int], Hashable]] = None, launch_counter=None):
@@ -65,6 +70,7 @@ class GraphedUNet:
         self._graphs: Dict[Hashable, tuple] = {}
         self._t: Dict[int, torch.Tensor] = {}
         self.replays = self.eager_calls = self.captures = self.replayed_launches = 0
+        self._pool = None  # one private memory pool shared by all phase graphs (their intermediates are never live together)
         if controller is not None:
             controller._graph_mode = True
 
@@ -99,8 +105,10 @@ class GraphedUNet:
         if n == 1:
             xs, ts, cs = x.clone(), td.clone(), ctx.clone()
             graph = torch.cuda.CUDAGraph()
+            if self._pool is None:
+                self._pool = torch.cuda.graph_pool_handle()
             before = self.launch_counter() if self.launch_counter else 0
-            with torch.cuda.graph(graph), torch.no_grad():
+            with torch.cuda.graph(graph, pool=self._pool), torch.no_grad():
                 out = self.unet(xs, ts, encoder_hidden_states=cs)["sample"]
             launches = (self.launch_counter() - before) if self.launch_counter else 0
             self._graphs[key] = (graph, xs, ts, cs, out, launches)

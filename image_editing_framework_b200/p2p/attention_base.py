@@ -130,6 +130,7 @@ class AttentionStore(AttentionControl):
         self.attention_store: Dict[str, List[torch.Tensor]] = {}
         self._slot = self._zero_slots()
         self._store_enabled = True
+        self._spare: Dict[str, List[torch.Tensor]] = {}  # buffers of the store before the last reset(), reused in place
 
     @staticmethod
     def get_empty_store():
@@ -147,7 +148,12 @@ class AttentionStore(AttentionControl):
         i = self._slot[key]
         self._slot[key] = i + 1
         if i == len(bufs):
-            bufs.append(torch.empty((rows * heads, n, m), dtype=torch.float32, device=device))
+            spare = self._spare.get(key, [])
+            shape = (rows * heads, n, m)
+            if i < len(spare) and tuple(spare[i].shape) == shape and spare[i].device == torch.device(device):
+                bufs.append(spare[i])  # same storage as before reset(): captured graphs keep pointing at live memory
+            else:
+                bufs.append(torch.empty(shape, dtype=torch.float32, device=device))
             return bufs[i], False
         return bufs[i], True
 
@@ -185,9 +191,18 @@ class AttentionStore(AttentionControl):
         # the first stored step allocates + overwrites the store, later ones accumulate into the same buffers
         return base + (("store", len(self.attention_store) != 0) if self._store_enabled else ("nostore",),)
 
+    def graph_advance(self) -> None:
+        if self._store_enabled and not self.attention_store and self._spare:
+            # replay of a first stored step after reset(): the kernels overwrote the previous buffers in place; publish
+            # them again the way _store_target does during an eager forward
+            self.attention_store = {key: list(bufs) for key, bufs in self._spare.items()}
+        super().graph_advance()
+
     def reset(self):
         super().reset()
         self.step_store = self.get_empty_store()
+        if self.attention_store:
+            self._spare = self.attention_store
         self.attention_store = {}
         self._slot = self._zero_slots()
 

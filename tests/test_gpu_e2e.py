@@ -206,3 +206,36 @@ def test_graph_replay_matches_eager(cuda, method):
     for a, b in zip(results[:n], results[n:]):
         assert psnr(b, a) >= 50.0, f"graph replay deviates from eager: PSNR {psnr(b, a):.1f} dB"
     assert stats["replays"] >= steps - 6 and stats["captures"] >= 1 and stats["replayed_launches"] > 0, stats
+
+
+def test_persistent_graph_runner_across_edits(cuda):
+    """One GraphedUNet reused over several images with controller.reset() in between: the map-store buffers are reused in place
+    (captured pointers stay valid), the third edit is pure replay, and every edit equals the eager result."""
+    from image_editing_framework_b200 import p2p, editing
+    from image_editing_framework_b200.graphs import GraphedUNet
+    from image_editing_framework_b200.standin import make_pipeline
+    from image_editing_framework_b200.standin.unet import UNetConfig
+    cfg = UNetConfig(**golden("p2p_localblend.pt")["config"])
+    prompts = ["a photo of a cat sitting on a bench", "a photo of a dog sitting on a bench"]
+    steps = 6
+    pipe = make_pipeline(cfg, seed=7, device=cuda)
+    common = dict(prompts=prompts, tokenizer=pipe.tokenizer, num_steps=steps, cross_replace_steps=0.8, self_replace_steps=0.5, device=cuda)
+    lats = [scenarios.latent(20 + i, (1, 4, 64, 64), cuda) for i in range(3)]
+    eager = []
+    for lat in lats:
+        ctrl = p2p.AttentionReplace(local_blend=p2p.LocalBlend(pipe.tokenizer, prompts, [["cat"], ["dog"]], device=cuda), **common)
+        eager.append(editing.p2p_edit(pipe, prompts, ctrl, lat, steps, 7.5).float().cpu())
+        p2p.unregister_attention_control(pipe, ctrl)
+    ctrl = p2p.AttentionReplace(local_blend=p2p.LocalBlend(pipe.tokenizer, prompts, [["cat"], ["dog"]], device=cuda), **common)
+    runner = GraphedUNet(pipe.unet, ctrl)
+    captures = []
+    for lat, want in zip(lats, eager):
+        ctrl.reset()
+        out = editing.p2p_edit(pipe, prompts, ctrl, lat, steps, 7.5, graphs=runner).float().cpu()
+        p2p.unregister_attention_control(pipe, ctrl)
+        captures.append(runner.captures)
+        assert psnr(out, want) >= 50.0, f"PSNR {psnr(out, want):.1f} dB"
+        assert ctrl.cur_step == steps
+    assert captures[2] == captures[1], f"third edit still captured: {captures}"
+    assert runner.replays >= 2 * steps
+    runner.close()
