@@ -30,7 +30,10 @@ class _Output(dict):
 
 
 class AttnProcessor:
-    """Plain attention (what an un-hooked diffusers Attention computes)."""
+    """Plain attention (what an un-hooked diffusers Attention computes). `use_sdpa = True` switches GPU calls to
+    F.scaled_dot_product_attention, diffusers 0.27's default AttnProcessor2_0 (full-size benchmarks); the default is the
+    spelled-out arithmetic the golden fixtures were generated with."""
+    use_sdpa = False
 
     def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None):
         residual = hidden_states
@@ -41,9 +44,15 @@ class AttnProcessor:
         q = attn.to_q(hidden_states)
         ctx = hidden_states if encoder_hidden_states is None else encoder_hidden_states
         k, v = attn.to_k(ctx), attn.to_v(ctx)
-        q, k, v = attn.head_to_batch_dim(q), attn.head_to_batch_dim(k), attn.head_to_batch_dim(v)
-        probs = attn.get_attention_scores(q, k, attention_mask)
-        out = attn.batch_to_head_dim(torch.bmm(probs, v))
+        if self.use_sdpa and q.is_cuda and attention_mask is None and not (attn.upcast_attention or attn.upcast_softmax):
+            h = attn.heads
+            q4, k4, v4 = (t.view(t.shape[0], t.shape[1], h, t.shape[2] // h).transpose(1, 2) for t in (q, k, v))
+            out = torch.nn.functional.scaled_dot_product_attention(q4, k4, v4, scale=attn.scale)
+            out = out.transpose(1, 2).reshape(q.shape[0], q.shape[1], -1)
+        else:
+            q, k, v = attn.head_to_batch_dim(q), attn.head_to_batch_dim(k), attn.head_to_batch_dim(v)
+            probs = attn.get_attention_scores(q, k, attention_mask)
+            out = attn.batch_to_head_dim(torch.bmm(probs, v))
         out = attn.to_out[1](attn.to_out[0](out))
         if input_ndim == 4:
             out = out.transpose(-1, -2).reshape(b, c, hh, ww)

@@ -11,10 +11,12 @@ import time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from image_editing_framework_b200 import p2p, masactrl, pnp, pix2pix_zero, editing, _cabi
-from image_editing_framework_b200.standin import make_pipeline, sd15_config
+from image_editing_framework_b200.standin import make_pipeline
+from image_editing_framework_b200.standin.unet import sd15_config, sd21_config, sdxl_config
 
 dev = torch.device("cuda:0")
 STEPS = int(sys.argv[1]) if len(sys.argv) > 1 else 50
+MODEL = sys.argv[2] if len(sys.argv) > 2 else "sd15"   # sd15 (512^2) | sd21 (768^2, BASELINE config 3) | sdxl (1024^2, config 4)
 PROMPTS = ["a photo of a cat sitting on a bench", "a photo of a dog sitting on a bench"]
 
 
@@ -24,13 +26,17 @@ def quiet(fn, *a, **kw):
 
 
 def main():
+    from image_editing_framework_b200.standin.unet import AttnProcessor
+    AttnProcessor.use_sdpa = True   # un-hooked layers (PnP patches 8 of 32) run what diffusers 0.27 runs on a GPU
+    cfg = {"sd15": sd15_config, "sd21": sd21_config, "sdxl": sdxl_config}[MODEL]()
+    hw = cfg.sample_size
     with torch.device(dev):
-        pipe = make_pipeline(sd15_config(), seed=0, device=dev, dtype=torch.bfloat16)
+        pipe = make_pipeline(cfg, seed=0, device=dev, dtype=torch.bfloat16)
     pipe.unet.to(memory_format=torch.channels_last)
     tok = pipe.tokenizer
     context = editing.encode_prompts(pipe, PROMPTS)
     g = torch.Generator().manual_seed(0)
-    lat1 = torch.randn(1, 4, 64, 64, generator=g).to(dev).to(torch.bfloat16)
+    lat1 = torch.randn(1, 4, hw, hw, generator=g).to(dev).to(torch.bfloat16)
     lat2 = torch.cat([lat1, lat1])
     common = dict(prompts=PROMPTS, tokenizer=tok, num_steps=STEPS, cross_replace_steps=0.8, self_replace_steps=0.6, device=dev)
 
@@ -98,11 +104,18 @@ def main():
         ("masactrl MutualSelfAttentionControl(4, 10)", masa_run(lambda: masactrl.MutualSelfAttentionControl(4, 10, total_steps=STEPS))),
         ("masactrl Union", masa_run(lambda: masactrl.MutualSelfAttentionControlUnion(4, 10, total_steps=STEPS))),
         ("masactrl MaskAuto", masa_run(lambda: masactrl.MutualSelfAttentionControlMaskAuto(4, 10, total_steps=STEPS, ref_token_idx=[5], cur_token_idx=[5]))),
-        ("pnp attn 0.5 / feature 0.8", lambda: editing.pnp_edit(pipe, PROMPTS, lat2, STEPS, 7.5, context=context, graphs=runner_for("pnp", None))),
+        ("pnp attn 0.5 / feature 0.8", lambda: editing.pnp_edit(pipe, PROMPTS, lat2, STEPS, 7.5, context=context, graphs=runner_for("pnp", None), xl=MODEL == "sdxl")),
         ("pix2pix-zero map-collection pass (B=2)", p2z_run),
     ]
+    if MODEL != "sd15":  # LocalBlend / MaskAuto read 16x16 maps of the SD-1.5 topology; MasaCtrl's layer table is model specific
+        keep = ("p2p EmptyControl", "p2p AttentionReplace 0.8/0.6", "p2p AttentionRefine", "pnp")
+        cases = [c for c in cases if c[0].startswith(keep)]
+        mt = "SDXL" if MODEL == "sdxl" else "SD"
+        sl = 64 if MODEL == "sdxl" else 10   # SDXL: the decoder's self-attention layers 64..69 (N=4096)
+        cases.append((f"masactrl MutualSelfAttentionControl(4, {sl}, model_type={mt})",
+                      masa_run(lambda: masactrl.MutualSelfAttentionControl(4, sl, total_steps=STEPS, model_type=mt))))
     for name, run in cases:
-        row = dict(method=name, ddim_steps=STEPS)
+        row = dict(method=name, model=MODEL, latent=hw, ddim_steps=STEPS)
         for graphs in (False, True):
             if graphs and name.startswith("pix2pix"):
                 continue
