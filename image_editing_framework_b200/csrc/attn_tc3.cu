@@ -36,6 +36,7 @@ constexpr int kRegsLow = 32, kRegsHigh = 112;  // pool = 640 threads x 96 regs a
 constexpr int ST = 3;
 constexpr int kTile = kTcChunkBytes;           // 16 KiB: one [128 x 64ch] box (head_dim <= 64)
 constexpr int kSmemXchg = 8 * 1024;            // floats: row-max exchange [2 parities][2 streams][2 halves][128] | row sums [2][2][128] | split merge [2][128]
+constexpr int kDefaultEmul = 0;  // measured: 1/6 of the pairs = +-0 %, 1/4 and 1/3 = -4 % (the pre-turn latency chain, not the MUFU, is critical)
 constexpr float kRescaleThreshold = 8.0f;
 
 template <bool SPLIT> struct Cfg3 {
@@ -47,7 +48,7 @@ template <bool SPLIT> struct Cfg3 {
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
-template <int DTYPE, bool SPLIT>
+template <int DTYPE, bool SPLIT, int EMUL>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                 const __grid_constant__ TcArgs a) {
@@ -293,8 +294,8 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       const float mc = m_used * c2;
       const float2 c2v = make_float2(c2, c2), nmc = make_float2(-mc, -mc);
-      scale_chunk(s0, c2v, nmc);   // FMA-pipe work, outside the MUFU turn
-      scale_chunk(s1, c2v, nmc);
+      scale_chunk_mix<EMUL>(s0, c2v, nmc);   // FMA-pipe work (incl. the emulated share of the exponentials), outside the MUFU turn
+      scale_chunk_mix<EMUL>(s1, c2v, nmc);
       if (!o_ready) {  // PV_t(j-1) must have finished reading P_t; wait for it BEFORE taking the exp turn, not inside it
         mbar_wait(bar_o(t), (j - 1) & 1);
         tc_fence_after();
@@ -303,11 +304,11 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (trace) tr[3] = clock64();
       float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
       uint32_t u[16];
-      exp_pack_chunk<E>(s0, u, acc0, acc1);
+      exp_pack_chunk_mix<E, EMUL>(s0, u, acc0, acc1);
       tmem_st16(tP, u);
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_x(t ^ 1));  // hand the MUFU over one chunk early
-      exp_pack_chunk<E>(s1, u, acc0, acc1);
+      exp_pack_chunk_mix<E, EMUL>(s1, u, acc0, acc1);
       tmem_st16(tP + 16, u);
       if (trace) tr[4] = clock64();
       tc_wait_st();
@@ -391,9 +392,9 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (cta_trace && threadIdx.x == 32) a.dbg[1541] = clock64();
 }
 
-template <int DTYPE, bool SPLIT>
-int launch_tc3(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, TcArgs a, int first, int count, int nq_blocks, cudaStream_t st) {
-  auto kern = attn_tc3_kernel<DTYPE, SPLIT>;
+template <int DTYPE, bool SPLIT, int EMUL>
+int launch_tc3e(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, TcArgs a, int first, int count, int nq_blocks, cudaStream_t st) {
+  auto kern = attn_tc3_kernel<DTYPE, SPLIT, EMUL>;
   static bool configured = false;
   if (!configured) {
     IEF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg3<SPLIT>::kSmemBytes));
@@ -405,6 +406,25 @@ int launch_tc3(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& 
   kern<<<count, kThreads, Cfg3<SPLIT>::kSmemBytes, st>>>(mq, mk, mv, a);
   IEF_LAUNCH_OK("attn_tc3_kernel");
   return IEF_OK;
+}
+
+// share of the exponentials computed on the FMA pipe: every EMUL-th column pair (0 = none). IEF_TC3_EMUL overrides (A/B runs).
+inline int emul_every() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("IEF_TC3_EMUL");
+    v = e ? atoi(e) : kDefaultEmul;
+    if (v != 0 && v != 6) v = kDefaultEmul;
+  }
+  return v;
+}
+
+template <int DTYPE, bool SPLIT>
+int launch_tc3(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, TcArgs a, int first, int count, int nq_blocks, cudaStream_t st) {
+  switch (emul_every()) {
+    case 6: return launch_tc3e<DTYPE, SPLIT, 6>(mq, mk, mv, a, first, count, nq_blocks, st);
+    default: return launch_tc3e<DTYPE, SPLIT, 0>(mq, mk, mv, a, first, count, nq_blocks, st);
+  }
 }
 
 template <int DTYPE>

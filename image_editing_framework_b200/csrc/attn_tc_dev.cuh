@@ -82,3 +82,51 @@ __device__ __forceinline__ void exp_pack_chunk(const uint32_t (&s)[32], uint32_t
     u[i + 1] = E::pack(x1.x, x1.y);
   }
 }
+
+// ---- part of the exponentials on the FMA + ALU pipes -------------------------------------------------------------------
+// MUFU.EX2 (16/clk/SM) is the binding unit of these kernels. exp2 of a pair by Cody-Waite range reduction (the 1.5*2^23
+// round-to-nearest trick) and a degree-3 minimax polynomial for 2^f on [-0.5, 0.5]: max relative error 7.5e-5, far below
+// the bf16 / fp16 rounding of P (tools/micro/exp_emul.cu). It costs ~11.5 issue cycles per element against 8 MUFU cycles, so
+// it only pays for a minority of the columns and when it runs OUTSIDE the MUFU turn, on the otherwise idle FMA pipe.
+__device__ __forceinline__ float2 exp2_fma(float2 t) {
+  const float2 magic = make_float2(12582912.f, 12582912.f), nmagic = make_float2(-12582912.f, -12582912.f), mone = make_float2(-1.f, -1.f);
+  const float2 c3 = make_float2(0.0551716685f, 0.0551716685f), c2 = make_float2(0.2426111251f, 0.2426111251f),
+               c1 = make_float2(0.6932609677f, 0.6932609677f), c0 = make_float2(0.9999280572f, 0.9999280572f);
+  t.x = fmaxf(t.x, -126.f);  // masked (-inf) and far-away keys end up as 2^-126 ~ 0 instead of wrapping the exponent field
+  t.y = fmaxf(t.y, -126.f);
+  const float2 r = fadd2(t, magic);
+  const float2 fi = fadd2(r, nmagic);
+  const float2 f = ffma2(fi, mone, t);
+  float2 p = ffma2(c3, f, c2);
+  p = ffma2(p, f, c1);
+  p = ffma2(p, f, c0);
+  float2 e;
+  e.x = __int_as_float((__float_as_int(r.x) << 23) + __float_as_int(p.x));
+  e.y = __int_as_float((__float_as_int(r.y) << 23) + __float_as_int(p.y));
+  return e;
+}
+
+// EVERY = 0: plain. EVERY = n: every n-th column pair of a chunk is exponentiated here (before the turn), the others only scaled.
+template <int EVERY> __device__ __forceinline__ constexpr bool emul_pair(int pair) { return EVERY > 0 && (pair % EVERY) == EVERY - 1; }
+
+template <int EVERY>
+__device__ __forceinline__ void scale_chunk_mix(uint32_t (&s)[32], float2 c2, float2 nmc) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    float2 x = ffma2(make_float2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), c2, nmc);
+    if (emul_pair<EVERY>(i / 2)) x = exp2_fma(x);
+    s[i] = __float_as_uint(x.x);
+    s[i + 1] = __float_as_uint(x.y);
+  }
+}
+
+template <typename E, int EVERY>
+__device__ __forceinline__ void exp_pack_chunk_mix(const uint32_t (&s)[32], uint32_t (&u)[16], float2& acc0, float2& acc1) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    float2 x = make_float2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1]));
+    if (!emul_pair<EVERY>(i)) { x.x = ief_exp2(x.x); x.y = ief_exp2(x.y); }
+    if (i & 1) acc1 = fadd2(acc1, x); else acc0 = fadd2(acc0, x);
+    u[i] = E::pack(x.x, x.y);
+  }
+}
