@@ -11,7 +11,7 @@ import os
 import subprocess
 import threading
 
-IEF_ABI_VERSION = 3
+IEF_ABI_VERSION = 4
 IEF_MAX_ROWS = 64
 
 IEF_BF16, IEF_F16, IEF_F32 = 0, 1, 2
@@ -43,6 +43,8 @@ class AttnParams(C.Structure):
         ("key_bias", C.c_void_p),
         ("bias_sel", C.POINTER(C.c_int32)),
         ("n_bias", C.c_int32),
+        ("workspace", C.c_void_p),
+        ("workspace_bytes", C.c_int64),
     ]
 
 
@@ -86,7 +88,7 @@ class UmmaProbeParams(C.Structure):
 
 # every symbol include/ief_b200.h declares; tests check the .so exports each one
 EXPORTS = (
-    "ief_attn_fwd", "ief_cross_attn_edit_fwd", "ief_store_accumulate", "ief_local_blend", "ief_mask_blend", "ief_cfg_ddim_step",
+    "ief_attn_fwd", "ief_attn_workspace_bytes", "ief_cross_attn_edit_fwd", "ief_store_accumulate", "ief_local_blend", "ief_mask_blend", "ief_cfg_ddim_step",
     "ief_umma_probe", "ief_abi_version", "ief_last_error", "ief_launch_count", "ief_last_attn_impl", "ief_check_device",
 )
 
@@ -142,6 +144,8 @@ def lib() -> C.CDLL:
         L.ief_check_device.restype = C.c_int
         L.ief_attn_fwd.argtypes = [C.POINTER(AttnParams), C.c_void_p]
         L.ief_attn_fwd.restype = C.c_int
+        L.ief_attn_workspace_bytes.argtypes = [C.POINTER(AttnParams)]
+        L.ief_attn_workspace_bytes.restype = C.c_int64
         L.ief_cross_attn_edit_fwd.argtypes = [C.POINTER(CrossParams), C.c_void_p]
         L.ief_cross_attn_edit_fwd.restype = C.c_int
         L.ief_store_accumulate.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int32, C.c_void_p]

@@ -322,6 +322,46 @@ int launch_tc(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& m
 
 }  // namespace
 
+// max_j |k_j| per 128-key tile of every (row, head), inflated by 0.1 %: with |q_i| it bounds the tile's scores (Cauchy-Schwarz),
+// which lets attn_tc3 (bf16) skip the running-maximum pass on most tiles. One thread per key, 16-byte loads.
+__global__ void __launch_bounds__(128) key_norm_kernel(const __nv_bfloat16* k, int64_t sb, int64_t sn, int64_t sh, int Nk, int d, int H, int ntb,
+                                                       float* out) {
+  const int tile = blockIdx.x, h = blockIdx.y, b = blockIdx.z, key = tile * 128 + threadIdx.x;
+  float acc = 0.f;
+  if (key < Nk) {
+    const __nv_bfloat16* row = k + (int64_t)b * sb + (int64_t)key * sn + (int64_t)h * sh;
+    for (int c = 0; c < d; c += 8) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(row + c));
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float lo = __uint_as_float(w[e] << 16), hi = __uint_as_float(w[e] & 0xffff0000u);
+        acc = fmaf(lo, lo, acc);
+        acc = fmaf(hi, hi, acc);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc = fmaxf(acc, __shfl_xor_sync(0xffffffffu, acc, o));
+  __shared__ float part[4];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) out[((int64_t)b * H + h) * ntb + tile] = sqrtf(fmaxf(fmaxf(part[0], part[1]), fmaxf(part[2], part[3]))) * 1.001f;
+}
+
+// Where the key-norm pre-pass pays (measured, profiles/r01_kernel_microbench_gen3b.jsonl): head dims 49..64 (no free accumulator
+// columns for the row-sum MMA, so the maximum pass is a larger share of the softmax instructions) and >= 24 key tiles (the
+// pre-pass launch costs 4-5 us): +3..7 %. At head_dim <= 48 and on short sequences it loses 3-13 %.
+static bool key_norm_prepass_pays(const ief_attn_params* p) {
+  return p->dtype == IEF_BF16 && p->d > 48 && p->d <= 64 && p->Nq >= 512 && ief_ceil_div(p->Nk, 128) * (p->k_src2 ? 2 : 1) >= 24 &&
+         p->key_bias == nullptr && p->probs_out == nullptr;
+}
+
+extern "C" int64_t ief_attn_workspace_bytes(const ief_attn_params* p) {
+  if (p == nullptr || !key_norm_prepass_pays(p)) return 0;
+  return (int64_t)p->B * p->H * ief_ceil_div(p->Nk, 128) * (int64_t)sizeof(float);
+}
+
 bool ief_attn_tc_supported(const ief_attn_params* p, const char** why) {
   static const char* w = "";
   if (why) *why = w;
@@ -360,6 +400,10 @@ int ief_attn_tc_launch(const ief_attn_params* p, const IefRowTable& rows, cudaSt
   const int fmt = p->dtype == IEF_BF16 ? 1 : 0;
   a.idesc_qk = make_idesc_f16(kBM, kBN, fmt, 0, 0);
   a.idesc_pv = make_idesc_f16(kBM, a.dv_mma, fmt, 0, 1);
+  a.idesc_sum = make_idesc_f16(kBM, 16, fmt, 0, 0);
+  a.knorm = nullptr;
+  a.knorm_tiles = 0;
+  a.sum_mma = (a.dv_mma <= 48 && getenv("IEF_TC3_NO_SUM_MMA") == nullptr) ? 1 : 0;
   a.scale_log2 = p->scale * kLog2e;
   a.rows = rows;
   a.dbg = ief_debug_trace_buffer();
@@ -397,7 +441,21 @@ int ief_attn_tc_launch(const ief_attn_params* p, const IefRowTable& rows, cudaSt
     if (force >= 0) mode = force;
     else if (t_hybrid < t_pair && t_hybrid <= t_split && full > 0 && rest > 0) mode = 2;
     else if (t_split < t_pair) mode = 1;
-    if (version >= 3) return ief_attn_tc3_launch(p, mq, mk, mv, a, mode, st);
+    if (version >= 3) {
+      const int ntb = ief_ceil_div(p->Nk, kBN);
+      static int use_skip = -1;
+      if (use_skip < 0) { const char* e = getenv("IEF_TC3_SKIPMAX"); use_skip = e ? atoi(e) : 1; }
+      if ((use_skip == 2 || (use_skip == 1 && key_norm_prepass_pays(p))) && p->dtype == IEF_BF16 && p->workspace != nullptr && p->workspace_bytes >= (int64_t)p->B * p->H * ntb * (int64_t)sizeof(float)) {
+        IEF_REQUIRE((reinterpret_cast<uintptr_t>(p->workspace) & 15) == 0, IEF_ERR_INVALID, "ief_attn_fwd: workspace must be 16-byte aligned");
+        float* kn = static_cast<float*>(p->workspace);
+        key_norm_kernel<<<dim3(ntb, p->H, p->B), 128, 0, st>>>(static_cast<const __nv_bfloat16*>(p->k.ptr), p->k.stride_b, p->k.stride_n, p->k.stride_h,
+                                                               p->Nk, p->d, p->H, ntb, kn);
+        IEF_LAUNCH_OK("key_norm_kernel");
+        a.knorm = kn;
+        a.knorm_tiles = ntb;
+      }
+      return ief_attn_tc3_launch(p, mq, mk, mv, a, mode, st);
+    }
     if (mode == 1) return ief_attn_tc2s_launch(p, mq, mk, mv, a, st);
   }
   if (version >= 2 && dch <= 2) return ief_attn_tc2_launch(p, mq, mk, mv, a, st);

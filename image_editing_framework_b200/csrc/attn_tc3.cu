@@ -35,20 +35,33 @@ constexpr int kThreads = 640;
 constexpr int kRegsLow = 32, kRegsHigh = 112;  // pool = 640 threads x 96 regs at launch (61440): 128*32 + 512*112 = 61440
 constexpr int ST = 3;
 constexpr int kTile = kTcChunkBytes;           // 16 KiB: one [128 x 64ch] box (head_dim <= 64)
+constexpr int kSmemOnes = 2 * 1024;            // [16 x 64] tile of 1.0 (K-major, SWIZZLE_128B footprint): B operand of the row-sum MMA
 constexpr int kSmemXchg = 8 * 1024;            // floats: row-max exchange [2 parities][2 streams][2 halves][128] | row sums [2][2][128] | split merge [2][128]
-constexpr int kDefaultEmul = 0;  // measured: 1/6 of the pairs = +-0 %, 1/4 and 1/3 = -4 % (the pre-turn latency chain, not the MUFU, is critical)
+#ifndef IEF_TC3_FINE_TRACE
+#define IEF_TC3_FINE_TRACE 0  // 1: extra clock64 stamps inside the pre-turn work (tools/tc3_trace.py prints them); costs ~2 %
+#endif
+#ifndef IEF_TC3_EMUL
+#define IEF_TC3_EMUL 0
+#endif
+constexpr int kDefaultEmul = IEF_TC3_EMUL;  // measured: 1/6 of the pairs = +-0 %, 1/4 and 1/3 = -4 % (the pre-turn latency chain, not the MUFU, is critical)
 constexpr float kRescaleThreshold = 8.0f;
+// bf16 only: a tile whose Cauchy-Schwarz score bound stays within 2^kSkipMargin of the first tile's smallest row maximum needs no
+// row-maximum pass at all (P and the fp32 accumulators have 8 exponent bits; see the softmax section)
+constexpr float kSkipMargin = 80.0f;
 
 template <bool SPLIT> struct Cfg3 {
   static constexpr int kQTiles = SPLIT ? 1 : 2;
   static constexpr int kRingTiles = SPLIT ? 2 : 1;                       // K (and V) tiles per ring stage
   static constexpr int kSmemData = kTile * (kQTiles + 2 * ST * kRingTiles);
-  static constexpr int kSmemBytes = kSmemData + kSmemXchg + 1024 + 256;
+  static constexpr int kSmemBytes = kSmemData + kSmemOnes + kSmemXchg + 1024 + 256;
 };
+
+// sqrt.approx (MUFU): sqrtf() would call the IEEE slow-path subroutine, which does not fit the 32-register helper warps
+__device__ __forceinline__ float approx_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
-template <int DTYPE, bool SPLIT, int EMUL>
+template <int DTYPE, bool SPLIT, int EMUL, bool SUMMMA, bool SKIP>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                 const __grid_constant__ TcArgs a) {
@@ -70,10 +83,12 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   auto sK = [&](int s, int t) { return base + kTile * (Cfg::kQTiles + RT * s + (SPLIT ? t : 0)); };
   auto sV = [&](int s, int t) { return base + kTile * (Cfg::kQTiles + RT * ST + RT * s + (SPLIT ? t : 0)); };
   float* stage_o = reinterpret_cast<float*>(base_ptr + kTile * Cfg::kQTiles);  // split merge staging: K ring stage 0 (32 KiB), [col][row]
-  float* xmax = reinterpret_cast<float*>(base_ptr + Cfg::kSmemData);          // [parity][stream][half][128]
+  const uint32_t sOnes = base + Cfg::kSmemData;
+  float* xmax = reinterpret_cast<float*>(base_ptr + Cfg::kSmemData + kSmemOnes);  // [parity][stream][half][128]
   float* xsum = xmax + 2 * 2 * 2 * 128;                                       // [stream][half][128]
   float* xml = xsum + 2 * 2 * 128;                                            // split merge: [0..127] max, [128..255] sum of stream 1
-  const uint32_t bar0 = base + Cfg::kSmemData + kSmemXchg;
+  float* xq = xml + 256;                                   // [2 streams][8 warps][2]: one-time (max |q|, min row max) exchange
+  const uint32_t bar0 = base + Cfg::kSmemData + kSmemOnes + kSmemXchg;
   const uint32_t bar_q = bar0;
   auto bar_s = [&](int t) { return bar0 + 8 + 8 * t; };    // S_t complete in TMEM
   auto bar_p = [&](int t) { return bar0 + 24 + 8 * t; };   // P_t written by the 256 softmax threads of stream t
@@ -89,6 +104,9 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nt = a.nt1 + a.nt2;
+  // bf16 + per-tile key-norm bounds from the pre-pass (ief_attn_tc_key_norms): tiles after the first skip the row-maximum pass
+  // when the bound proves that harmless (see the softmax section)
+  constexpr bool skip_guard = SKIP;
   // key tiles per stream: pair -> both streams see all nt tiles; split -> [0, nt0) and [nt0, nt)
   const int nt0 = SPLIT ? (nt + 1) >> 1 : nt, nt1 = SPLIT ? nt - nt0 : nt;
   auto stream_nt = [&](int t) { return t == 0 ? nt0 : nt1; };
@@ -123,6 +141,15 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp == 1) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
+  }
+  if constexpr (SUMMMA) {
+    // Row sums on the tensor pipe: l = P x ones lands in the 16 accumulator columns after O (free when head_dim <= 48), in
+    // the same fp32 accumulation and under the same lazy rescale as O. That removes the 32 packed adds per row and tile from
+    // the softmax warps, whose instruction issue — not the MUFU alone — bounds this kernel.
+    uint32_t* ones = reinterpret_cast<uint32_t*>(base_ptr + Cfg::kSmemData);
+    const uint32_t one2 = DTYPE == IEF_BF16 ? 0x3f803f80u : 0x3c003c00u;
+    for (int i = threadIdx.x; i < kSmemOnes / 4; i += kThreads) ones[i] = one2;
+    fence_proxy_async();
   }
   tc_fence_before();
   __syncthreads();
@@ -177,6 +204,11 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
       for (int k = 0; k < kBN / 16; ++k)
         umma_ts(tmem_base + 384 + 64 * t, tmem_base + 256 + 64 * t + k * 8, desc_v | ((sV(s, t) + k * 2048) >> 4), a.idesc_pv, acc || (k > 0));
+      if constexpr (SUMMMA) {
+#pragma unroll
+        for (int k = 0; k < kBN / 16; ++k)  // every 16-key step multiplies the same all-ones [16 x 16] block
+          umma_ts(tmem_base + 384 + 64 * t + a.dv_mma, tmem_base + 256 + 64 * t + k * 8, desc_k | ((sOnes + (k & 3) * 32) >> 4), a.idesc_sum, acc || (k > 0));
+      }
     };
     mbar_wait(bar_q, 0);
     mbar_wait(bar_kf(0), 0);
@@ -235,18 +267,45 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t tO = tmem_base + 384 + 64 * t + lane_off;
     const float c2 = a.scale_log2;
     float m_used = -INFINITY, l = 0.f;
-    const int nchunk_o = a.dv_mma >> 4;
+    float qn_max = INFINITY, m_floor = -INFINITY;  // stream-wide max |q_row| and min first-tile row maximum (scaled): the skip test
+    float qn_row = 0.f;
+    if constexpr (skip_guard) {
+      // |q_row| from the Q tile in shared memory (chunk order rotated by lane against bank conflicts), before the score
+      // registers go live
+      mbar_wait(bar_q, 0);
+      const uint8_t* qrow = base_ptr + (sQ(SPLIT ? 0 : t) - base) + row * 128;
+      float acc = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint4 v = *reinterpret_cast<const uint4*>(qrow + (((c + lane) & 7) << 4));
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float lo = __uint_as_float(w[e] << 16), hi = __uint_as_float(w[e] & 0xffff0000u);
+          acc = fmaf(lo, lo, acc);
+          acc = fmaf(hi, hi, acc);
+        }
+      }
+      qn_row = approx_sqrt(acc) * 1.001f;
+    }
+    constexpr bool sum_mma = SUMMMA;
+    const int nchunk_o = (a.dv_mma >> 4) + (sum_mma ? 1 : 0);  // accumulator chunks touched by the lazy rescale (the row sums ride along in the chunk after O)
     const int my_nt = stream_nt(t);
 
     // Turn protocol: exp sections alternate 0(0) 1(0) 0(1) 1(1) ...; stream 0 waits for stream 1's previous section, stream
     // 1 for stream 0's current one. In the split flavour stream 1 may be one step short (odd tile count): stream 0's last
     // grant then simply goes unused.
     for (int j = 0; j < my_nt; ++j) {
-      int jj, kb_unused, vb_unused;
-      kv_coord(global_tile(t, j), jj, kb_unused, vb_unused);
+      int jj, kb_tile, vb_unused;
+      kv_coord(global_tile(t, j), jj, kb_tile, vb_unused);
       const int vc = min(kBN, a.Nk - jj * kBN);
+      float kn_cur = 0.f;  // requested here, needed after the score load: its latency hides behind the barrier wait and tcgen05.ld
+      if constexpr (skip_guard) kn_cur = __ldg(a.knorm + ((int64_t)kb_tile * a.H + h) * a.knorm_tiles + jj);
       const bool trace = a.dbg != nullptr && lin == 0 && row == 0 && half == 0 && j < 64;
       long long* tr = trace ? a.dbg + (t * 64 + j) * 8 : nullptr;
+#if IEF_TC3_FINE_TRACE
+      long long* tr2 = trace ? a.dbg + 1024 + (t * 64 + j) * 4 : nullptr;  // sub-phases of the pre-turn work
+#endif
       if (trace) tr[0] = clock64();
       mbar_wait(bar_s(t), j & 1);
       tc_fence_after();
@@ -263,52 +322,97 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mask_chunk(s0, 64 * half, vc);
         mask_chunk(s1, 64 * half + 32, vc);
       }
-      // row maximum: own 64 columns, then exchange with the other half of the row
-      const float lmax = fmaxf(max_chunk(s0, -INFINITY), max_chunk(s1, -INFINITY));
-      float* xm = xmax + ((j & 1) * 4 + t * 2) * 128;
-      xm[half * 128 + row] = lmax;
-      named_bar_sync(1 + t, 256);
-      const float tmax = fmaxf(lmax, xm[(half ^ 1) * 128 + row]);
       bool o_ready = j == 0;
-      if (j == 0) {
-        m_used = tmax;
-      } else {
-        const float m_new = fmaxf(m_used, tmax);
-        const bool need = (m_new - m_used) * c2 > kRescaleThreshold;
-        if (__any_sync(0xffffffffu, need)) {  // both halves of a row see identical values and take the same decision
-          mbar_wait(bar_o(t), (j - 1) & 1);
-          tc_fence_after();
-          o_ready = true;
-          const float alpha = ief_exp2((m_used - m_new) * c2);
-          for (int cc = half; cc < nchunk_o; cc += 2) {  // this half's share of the O columns
-            uint32_t r[16];
-            tmem_ld16(tO + 16 * cc, r);
-            tc_wait_ld();
+      // bf16: P and the fp32 accumulators carry 8 exponent bits, so the running maximum only has to keep exp2() in range, not
+      // near 1. qn_max * kn(tile) * c2 bounds every scaled score of the tile (Cauchy-Schwarz); while it stays within
+      // 2^kSkipMargin of the smallest first-tile row maximum, m_used is left alone and the tile needs no maximum pass, no
+      // exchange between the column halves and no rescale decision. The test is identical in all 256 threads of the stream.
+      bool exact = true;
+      if constexpr (skip_guard) exact = j == 0 || qn_max * kn_cur * c2 - m_floor > kSkipMargin;
+      if (exact) {
+        // row maximum: own 64 columns, then exchange with the other half of the row
+        const float lmax = fmaxf(max_chunk(s0, -INFINITY), max_chunk(s1, -INFINITY));
+#if IEF_TC3_FINE_TRACE
+        if (trace) tr2[0] = clock64();
+#endif
+        float* xm = xmax + ((j & 1) * 4 + t * 2) * 128;
+        xm[half * 128 + row] = lmax;
+        named_bar_sync(1 + t, 256);
+#if IEF_TC3_FINE_TRACE
+        if (trace) tr2[1] = clock64();
+#endif
+        const float tmax = fmaxf(lmax, xm[(half ^ 1) * 128 + row]);
+        if (j == 0) {
+          m_used = tmax;
+          if constexpr (skip_guard) {
+            // one-time: stream-wide max |q_row| and min first-tile row maximum through shared memory
+            float qn = qn_row, mf = tmax * c2;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-            tmem_st16(tO + 16 * cc, r);
+            for (int o = 16; o > 0; o >>= 1) {
+              qn = fmaxf(qn, __shfl_xor_sync(0xffffffffu, qn, o));
+              mf = fminf(mf, __shfl_xor_sync(0xffffffffu, mf, o));
+            }
+            float* xw = xq + t * 16;
+            if (lane == 0) {
+              xw[2 * (idx & 7)] = qn;
+              xw[2 * (idx & 7) + 1] = mf;
+            }
+            named_bar_sync(1 + t, 256);
+            qn_max = xw[0];
+            m_floor = xw[1];
+#pragma unroll
+            for (int w8 = 1; w8 < 8; ++w8) {
+              qn_max = fmaxf(qn_max, xw[2 * w8]);
+              m_floor = fminf(m_floor, xw[2 * w8 + 1]);
+            }
           }
-          l *= alpha;
-          m_used = m_new;
+        } else {
+          const float m_new = fmaxf(m_used, tmax);
+          const bool need = (m_new - m_used) * c2 > kRescaleThreshold;
+          if (__any_sync(0xffffffffu, need)) {  // both halves of a row see identical values and take the same decision
+            mbar_wait(bar_o(t), (j - 1) & 1);
+            tc_fence_after();
+            o_ready = true;
+            const float alpha = ief_exp2((m_used - m_new) * c2);
+            for (int cc = half; cc < nchunk_o; cc += 2) {  // this half's share of the O columns
+              uint32_t r[16];
+              tmem_ld16(tO + 16 * cc, r);
+              tc_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+              tmem_st16(tO + 16 * cc, r);
+            }
+            l *= alpha;
+            m_used = m_new;
+          }
         }
       }
+#if IEF_TC3_FINE_TRACE
+      if (trace) tr2[2] = clock64();
+#endif
       const float mc = m_used * c2;
       const float2 c2v = make_float2(c2, c2), nmc = make_float2(-mc, -mc);
       scale_chunk_mix<EMUL>(s0, c2v, nmc);   // FMA-pipe work (incl. the emulated share of the exponentials), outside the MUFU turn
       scale_chunk_mix<EMUL>(s1, c2v, nmc);
+#if IEF_TC3_FINE_TRACE
+      if (trace) tr[6] = clock64();
+#endif
       if (!o_ready) {  // PV_t(j-1) must have finished reading P_t; wait for it BEFORE taking the exp turn, not inside it
         mbar_wait(bar_o(t), (j - 1) & 1);
         tc_fence_after();
       }
+#if IEF_TC3_FINE_TRACE
+      if (trace) tr[7] = clock64();
+#endif
       if (t == 1 || j > 0) mbar_wait(bar_x(t), (t == 1 ? j : j - 1) & 1);   // ordered exp sections
       if (trace) tr[3] = clock64();
       float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
       uint32_t u[16];
-      exp_pack_chunk_mix<E, EMUL>(s0, u, acc0, acc1);
+      if constexpr (sum_mma) exp_pack_chunk_nosum<E, EMUL>(s0, u); else exp_pack_chunk_mix<E, EMUL>(s0, u, acc0, acc1);
       tmem_st16(tP, u);
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_x(t ^ 1));  // hand the MUFU over one chunk early
-      exp_pack_chunk_mix<E, EMUL>(s1, u, acc0, acc1);
+      if constexpr (sum_mma) exp_pack_chunk_nosum<E, EMUL>(s1, u); else exp_pack_chunk_mix<E, EMUL>(s1, u, acc0, acc1);
       tmem_st16(tP + 16, u);
       if (trace) tr[4] = clock64();
       tc_wait_st();
@@ -324,11 +428,19 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tc_fence_after();
     }
     if (cta_trace && warp == 4 && lane == 0) a.dbg[1539] = clock64();
-    // ---- epilogue: merge the two column halves' row sums ...
-    float* xs = xsum + t * 2 * 128;
-    xs[half * 128 + row] = l;
-    named_bar_sync(1 + t, 256);
-    float lrow = l + xs[(half ^ 1) * 128 + row];
+    // ---- epilogue: row sum = first accumulator column after O (row-sum MMA) or the merge of the two column halves' partial sums ...
+    float lrow;
+    if constexpr (sum_mma) {
+      uint32_t r[16];
+      tmem_ld16(tO + a.dv_mma, r);
+      tc_wait_ld();
+      lrow = my_nt > 0 ? __uint_as_float(r[0]) : 0.f;
+    } else {
+      float* xs = xsum + t * 2 * 128;
+      xs[half * 128 + row] = l;
+      named_bar_sync(1 + t, 256);
+      lrow = l + xs[(half ^ 1) * 128 + row];
+    }
     const int nchunk_d = (a.d + 15) >> 4;
     float wmine = 1.f, wother = 0.f;
     if constexpr (SPLIT) {
@@ -392,9 +504,9 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (cta_trace && threadIdx.x == 32) a.dbg[1541] = clock64();
 }
 
-template <int DTYPE, bool SPLIT, int EMUL>
-int launch_tc3e(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, TcArgs a, int first, int count, int nq_blocks, cudaStream_t st) {
-  auto kern = attn_tc3_kernel<DTYPE, SPLIT, EMUL>;
+template <int DTYPE, bool SPLIT, bool SUMMMA, bool SKIP>
+int launch_tc3s(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, TcArgs a, int first, int count, int nq_blocks, cudaStream_t st) {
+  auto kern = attn_tc3_kernel<DTYPE, SPLIT, kDefaultEmul, SUMMMA, SKIP>;
   static bool configured = false;
   if (!configured) {
     IEF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg3<SPLIT>::kSmemBytes));
@@ -408,23 +520,15 @@ int launch_tc3e(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap&
   return IEF_OK;
 }
 
-// share of the exponentials computed on the FMA pipe: every EMUL-th column pair (0 = none). IEF_TC3_EMUL overrides (A/B runs).
-inline int emul_every() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("IEF_TC3_EMUL");
-    v = e ? atoi(e) : kDefaultEmul;
-    if (v != 0 && v != 6) v = kDefaultEmul;
-  }
-  return v;
-}
-
 template <int DTYPE, bool SPLIT>
 int launch_tc3(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, TcArgs a, int first, int count, int nq_blocks, cudaStream_t st) {
-  switch (emul_every()) {
-    case 6: return launch_tc3e<DTYPE, SPLIT, 6>(mq, mk, mv, a, first, count, nq_blocks, st);
-    default: return launch_tc3e<DTYPE, SPLIT, 0>(mq, mk, mv, a, first, count, nq_blocks, st);
+  if constexpr (DTYPE == IEF_BF16) {
+    if (a.knorm != nullptr)  // key-norm pre-pass available: the variant that skips provably harmless row-maximum passes
+      return a.sum_mma ? launch_tc3s<DTYPE, SPLIT, true, true>(mq, mk, mv, a, first, count, nq_blocks, st)
+                       : launch_tc3s<DTYPE, SPLIT, false, true>(mq, mk, mv, a, first, count, nq_blocks, st);
   }
+  return a.sum_mma ? launch_tc3s<DTYPE, SPLIT, true, false>(mq, mk, mv, a, first, count, nq_blocks, st)
+                   : launch_tc3s<DTYPE, SPLIT, false, false>(mq, mk, mv, a, first, count, nq_blocks, st);
 }
 
 template <int DTYPE>

@@ -107,7 +107,7 @@ __device__ __forceinline__ float2 exp2_fma(float2 t) {
 }
 
 // EVERY = 0: plain. EVERY = n: every n-th column pair of a chunk is exponentiated here (before the turn), the others only scaled.
-template <int EVERY> __device__ __forceinline__ constexpr bool emul_pair(int pair) { return EVERY > 0 && (pair % EVERY) == EVERY - 1; }
+template <int EVERY> __device__ __forceinline__ constexpr bool emul_pair(int pair) { return EVERY > 0 && (pair % (EVERY > 0 ? EVERY : 1)) == EVERY - 1; }
 
 template <int EVERY>
 __device__ __forceinline__ void scale_chunk_mix(uint32_t (&s)[32], float2 c2, float2 nmc) {
@@ -127,6 +127,17 @@ __device__ __forceinline__ void exp_pack_chunk_mix(const uint32_t (&s)[32], uint
     float2 x = make_float2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1]));
     if (!emul_pair<EVERY>(i)) { x.x = ief_exp2(x.x); x.y = ief_exp2(x.y); }
     if (i & 1) acc1 = fadd2(acc1, x); else acc0 = fadd2(acc0, x);
+    u[i] = E::pack(x.x, x.y);
+  }
+}
+
+// the same without the row sum (it is computed by the tensor pipe: P x ones)
+template <typename E, int EVERY>
+__device__ __forceinline__ void exp_pack_chunk_nosum(const uint32_t (&s)[32], uint32_t (&u)[16]) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    float2 x = make_float2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1]));
+    if (!emul_pair<EVERY>(i)) { x.x = ief_exp2(x.x); x.y = ief_exp2(x.y); }
     u[i] = E::pack(x.x, x.y);
   }
 }

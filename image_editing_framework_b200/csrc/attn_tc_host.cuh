@@ -14,10 +14,14 @@ struct TcArgs {
   int32_t ksteps_qk;       // ceil(d/16)
   int32_t dv_mma;          // N of the PV MMA (>= d, multiple of 16)
   uint32_t idesc_qk, idesc_pv;
+  uint32_t idesc_sum;      // attn_tc3: [128 x 16] = P x ones (row sums on the tensor pipe), K-major B operand
+  int32_t sum_mma;         // attn_tc3: 1 when dv_mma <= 48: the 16 columns after O in each 64-column accumulator hold the row sums
   float scale_log2;
   int32_t perm_q[3], perm_k[3], perm_v[3];  // which of (token, head, row) feeds TMA coordinate 1..3
   int32_t work_offset;  // attn_tc3: first linear work item (q block + nq_blocks * (head + H * row)) of this launch
   int32_t nq_blocks;    // attn_tc3: query blocks per (row, head) in this launch's flavour
+  const float* knorm;   // attn_tc3, bf16: [B][H][knorm_tiles] max key norm per 128-key tile (pre-pass), or null
+  int32_t knorm_tiles;
   IefRowTable rows;
   long long* dbg;  // optional clock64 trace of CTA (0,0,0), see ief_debug_set_trace_buffer
 };

@@ -5,6 +5,9 @@ here="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 out="${1:-$here/..}"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr)
+# experiment switches, e.g. IEF_EXTRA_NVCC_FLAGS="-DIEF_TC3_FINE_TRACE=1"
+read -r -a EXTRA <<< "${IEF_EXTRA_NVCC_FLAGS:-}"
+FLAGS+=("${EXTRA[@]}")
 objs=()
 pids=()
 mkdir -p "$here/build"

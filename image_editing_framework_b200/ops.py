@@ -98,6 +98,10 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, sca
         p.probs_out = probs_out.data_ptr()
         p.probs_accum = 1 if probs_accum else 0
     with torch.cuda.device(q.device):
+        ws_bytes = _cabi.lib().ief_attn_workspace_bytes(C.byref(p)) if impl != IEF_IMPL_MMA else 0
+        if ws_bytes > 0:  # scratch for the key-norm pre-pass of the bf16 tcgen05 kernel (caching allocator: no cudaMalloc per call)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=q.device)
+            p.workspace, p.workspace_bytes = ws.data_ptr(), ws_bytes
         _cabi.check("ief_attn_fwd", _cabi.lib().ief_attn_fwd(C.byref(p), _stream()))
     return out
 

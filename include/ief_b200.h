@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define IEF_ABI_VERSION 3
+#define IEF_ABI_VERSION 4
 #define IEF_MAX_ROWS 64  /* max UNet batch rows per call (reference uses 1, 2 or 4) */
 #define IEF_MAX_WORDS 77 /* CLIP context length, p2p/model/ptp_utils.py:8 MAX_NUM_WORDS */
 
@@ -93,7 +93,15 @@ typedef struct ief_attn_params {
                               238-246; "masked" keys carry finfo.min, as there). mma kernel only; no second K/V block. */
   const int32_t* bias_sel; /* HOST [B] or NULL (= no bias): row b uses key_bias[bias_sel[b]]; <0 = no bias for that row */
   int32_t n_bias;
+  void* workspace;         /* optional device scratch of >= ief_attn_workspace_bytes(p) bytes (16-byte aligned), or NULL. With it the
+                              bf16 tcgen05 kernel runs a small pre-pass (max key norm per 128-key tile) whose Cauchy-Schwarz score
+                              bound lets most tiles skip the running-maximum pass; results are the same softmax. Contents are
+                              only meaningful during the call. */
+  int64_t workspace_bytes;
 } ief_attn_params;
+
+/* Scratch size ief_attn_fwd can make use of for these parameters (0 = none). */
+int64_t ief_attn_workspace_bytes(const ief_attn_params* p);
 
 int ief_attn_fwd(const ief_attn_params* p, void* stream);
 

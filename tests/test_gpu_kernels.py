@@ -109,6 +109,30 @@ def test_attn_large_logits_lazy_rescale(cuda):
     assert (got.float().cpu() - want).abs().max().item() < TOL
 
 
+@pytest.mark.parametrize("case", ["plain", "late_large_keys", "huge_norms", "union"])
+def test_attn_tcgen05_max_skipping_guard(cuda, case):
+    """bf16, 48 < head_dim <= 64, >= 24 key tiles: the kernel runs a key-norm pre-pass and skips the running-maximum pass on tiles
+    whose Cauchy-Schwarz score bound is harmless. The softmax must stay the same: (a) ordinary data, (b) later tiles with far
+    larger scores than the first tile (the stale maximum is kept, probabilities grow up to ~2^40), (c) norms so large that
+    the bound fails and every tile takes the exact path, (d) two key/value blocks."""
+    B, H, N, M, d = 2, 2, 640, 3200, 64
+    q, k, v = _qkv(B, N, M, H, d, 31, spread=6.0 if case == "huge_norms" else 1.0)
+    if case == "late_large_keys":
+        k = k.clone()
+        k[:, 1500:] = (k[:, 1500:].float() * 6).to(k.dtype)
+    kw = dict(k_src=[0, 0], v_src=[0, 0], k_src2=[0, 1], v_src2=[0, 1]) if case == "union" else {}
+    if case == "union":
+        q, k, v = q[:, :, :], k[:, :1600].contiguous(), v[:, :1600].contiguous()
+    scale = d ** -0.5
+    want = orc.indexed_attention(q, k, v, H, scale, **kw)
+    got = ops.attention(q.to(cuda), k.to(cuda), v.to(cuda), H, scale, impl=ops.IEF_IMPL_TCGEN05, **kw)
+    torch.cuda.synchronize()
+    assert _cabi.last_attn_impl() == "tcgen05"
+    assert torch.isfinite(got).all()
+    err = (got.float().cpu() - want).abs().max().item()
+    assert err < TOL, f"{case}: max abs err {err}"
+
+
 def test_attn_auto_dispatch(cuda):
     q, k, v = _qkv(2, 4096, 4096, 8, 40, 0)
     ops.attention(q.to(cuda), k.to(cuda), v.to(cuda), 8, 40 ** -0.5)

@@ -36,7 +36,7 @@ def test_struct_sizes_match_header_layout():
     import ctypes as C
     # 4 tensor4 (32 B each) + 6 int32 + float + int32 (=160) + 5 pointers + ptr + int32(+pad) + 2 pointers
     assert C.sizeof(_cabi.Tensor4) == 32
-    assert C.sizeof(_cabi.AttnParams) == 128 + 32 + 5 * 8 + 8 + 8 + 8 + 8 + 8 + 8 + 8
+    assert C.sizeof(_cabi.AttnParams) == 128 + 32 + 5 * 8 + 8 + 8 + 8 + 8 + 8 + 8 + 8 + 8 + 8
     assert C.sizeof(_cabi.CrossParams) == 128 + 32 + 8 + 8 + 8 + 7 * 8 + 8 + 8 + 8
 
 
