@@ -308,7 +308,7 @@ def run_ours(args):
         "e2e": {"value": round(world * args.steps / (ms_e2e * 1e-3), 4), "unit": "edits/s",
                 "h2d_bytes_per_step": host_latent.numel() * 2 + host_context.numel() * 2, "d2h_bytes_per_step": host_out.numel() * 2},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "kernel": "tcgen05 gen-3 controlled self-attention (attn_tc3_kernel; one call = full waves as 256-row pair CTAs + remainder as split-KV CTAs, bf16) B=4 H=8 N=4096 d=40", "timed_in": "eager pass of the same edits" if use_graphs else "the timed region",
+        "roofline": {"bound": "tensor", "kernel": "tcgen05 gen-3b controlled self-attention (attn_tc3_kernel, row sums on the tensor pipe; one call = full waves as 256-row pair CTAs + remainder as split-KV CTAs, bf16) B=4 H=8 N=4096 d=40", "timed_in": "eager pass of the same edits" if use_graphs else "the timed region",
                      "achieved": round(achieved, 1) if achieved else None, "peak": peak, "peak_source": f"{pk_src} bf16_tflops_sustained",
                      "unit": "TFLOP/s", "frac": round(achieved / peak, 4) if achieved else None,
                      "frac_of_burst_peak": round(achieved / pk["bf16_tflops"], 4) if achieved else None,
@@ -323,7 +323,7 @@ def run_ours(args):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from profiles/ (one ncu --set full capture); None until captured
-TRAFFIC_BYTES_PER_LAUNCH = 26.63e6  # profiles/r01_attn_tc3_hybrid_sd15_64_ncu_full.txt: dram read 20.10 MB (pair launch) + 6.53 MB (split-KV launch), writes < 1 KB (O stays in L2)
+TRAFFIC_BYTES_PER_LAUNCH = 26.62e6  # profiles/r01_attn_tc3_summma_sd15_64_ncu_full.txt: dram read 20.10 MB (pair launch) + 6.53 MB (split-KV launch), writes < 1 KB (O stays in L2)
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
