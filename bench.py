@@ -110,6 +110,9 @@ class KernelTimer:
         def timed(q, k, v, heads, scale, **kw):
             if self.on and (q.shape[0], heads, q.shape[1], q.shape[2] // heads) == self.shape and kw.get("probs_out") is None:
                 s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                # the eager pass is host-bound (the GPU idles between launches): keep it busy for ~50 us so that the host has
+                # enqueued the launches before the start event fires and the pair brackets device time only
+                torch.cuda._sleep(100000)
                 s.record()
                 out = self.inner(q, k, v, heads, scale, **kw)
                 e.record()
@@ -220,9 +223,12 @@ def run_ours(args):
             editor = masactrl.MutualSelfAttentionControl(START_STEP, START_LAYER, total_steps=args.ddim_steps)
             regs[0](pipe, editor)
             latents = torch.cat([lat, lat])
-            for t in ts:
+            for i, t in enumerate(ts):
+                # NVTX range for `ncu --nvtx --nvtx-include "edit_ctrl/"`: one MasaCtrl-controlled B=4 forward + step update
+                torch.cuda.nvtx.range_push("edit_ctrl" if i >= START_STEP else "edit_plain")
                 eps = unet_fwd(torch.cat([latents] * 2), tstep(t), ctx)
                 latents = fused.step(eps, t, latents, GUIDANCE)
+                torch.cuda.nvtx.range_pop()
             regs[1](pipe, editor)
         return latents
 
