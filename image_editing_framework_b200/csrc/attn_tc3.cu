@@ -20,6 +20,14 @@
 // The two streams' exp sections are strictly ORDERED (the ping-pong of FlashAttention-3/4): left alone they fall into
 // lock-step and idle the MUFU together. Scale/shift (FMA pipe) happens before a stream takes its turn, and the turn is
 // handed over one 32-column chunk early so the other stream's wake-up overlaps the tail.
+//
+// Measured (tools/tc3_trace.py): what bounds the kernel is the instruction stream of the four softmax warps per sub-partition,
+// not the MUFU alone, so two compile-time variants delete instructions from it:
+//   SUMMMA  head_dim <= 48: row sums come from an extra [128 x 16] = P x ones MMA into the accumulator columns left free after O
+//           (same fp32 accumulation and lazy rescale as O) instead of 32 packed adds per row and tile
+//   SKIP    bf16 with a key-norm pre-pass (TcArgs::knorm): tiles whose Cauchy-Schwarz score bound is provably harmless skip the
+//           running-maximum pass, the exchange between the column halves and the rescale decision
+// (the same switches as run-time branches cost 8-13 %).
 #include "ief_common.cuh"
 #include "ptx_sm100.cuh"
 #include "attn_tc_host.cuh"

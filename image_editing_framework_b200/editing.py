@@ -4,6 +4,8 @@ These mirror the reference call sequences so end-to-end parity tests and bench.p
   p2p_edit       p2p/model/sd_utils.py:24-79        (register -> loop: unet(cat[latents]*2) -> CFG -> scheduler.step -> step_callback)
   masactrl_edit  masactrl/model/sd_utils.py:25-124
   pnp_edit       pnp/model/sd_utils.py:23-115       (register_time per step, q/k + feature injection schedules)
+  pix2pix_zero_edit  pix2pix-zero/model/sd_utils.py:86-182  (map-collection loop, then per step: guidance gradient on the latents
+                                                     from the cross-attention maps -> SGD step -> recomputed noise -> DDIM step)
 Orchestration only — every attention call goes through the registered closures, every step update through FusedDDIM.
 """
 from __future__ import annotations
@@ -110,3 +112,56 @@ def pnp_edit(model, prompts: List[str], latents: torch.Tensor, num_inference_ste
     finally:
         reg[3](model)
         reg[4](model)
+
+
+def _cross_modules(unet):
+    return [(n, m) for n, m in unet.named_modules() if type(m).__name__ == "Attention" and "attn2" in n]
+
+
+def pix2pix_zero_edit(model, embeds_src: torch.Tensor, embeds_edit: torch.Tensor, latents: torch.Tensor, num_inference_steps: int = 50,
+                      guidance_scale: float = 7.5, guidance_amount: float = 0.1, only_sample: bool = False, graphs: bool = False,
+                      map_dtype: torch.dtype = torch.float32):
+    """Pix2Pix-zero's two denoising loops on latents (pix2pix-zero/model/sd_utils.py:86-182). The UNet must carry MyAttnProcessor
+    (prep_unet). embeds_*: [uncond, cond] context pairs ([2, 77, C]); latents: [1, 4, h, w]. Returns (reconstruction latents,
+    edited latents).
+
+    Differences from the reference, none of them arithmetic: the reference cross-attention maps of loop 1 stay on the device
+    (the reference moves 16 maps per step to the host with a blocking `.cpu()` and back in loop 2, :105-110,169); loop 1 and the
+    recomputed-noise pass of loop 2 run the fused kernels (optionally replayed from a CUDA graph); only the guidance pass, which
+    needs d loss / d latents, runs differentiable torch arithmetic."""
+    model.scheduler.set_timesteps(num_inference_steps)
+    fused = FusedDDIM(model.scheduler)
+    ts = model.scheduler.timesteps.tolist()
+    cross = _cross_modules(model.unet)
+    latents_init = latents.clone()
+    runner = GraphedUNet(model.unet, None, None, launch_counter=_cabi.launch_count) if graphs else None
+    ref_maps = {}
+    with torch.no_grad():  # loop 1: reference maps (:92-122)
+        for t in ts:
+            x = torch.cat([latents] * 2)
+            eps = runner(x, t, embeds_src) if runner is not None else model.unet(x, t, encoder_hidden_states=embeds_src)["sample"]
+            # a replayed graph rewrites the same attn_probs buffers every step: the cache must own its copy either way
+            ref_maps[t] = [m.attn_probs.detach().to(map_dtype, copy=True) for _, m in cross]
+            latents = fused.step(eps, t, latents, guidance_scale)
+    latents_rec = latents
+    if only_sample:
+        if runner is not None:
+            runner.close()
+        return latents_rec, None
+    latents = latents_init
+    for t in ts:  # loop 2: cross-attention guidance (:152-182)
+        x_in = torch.cat([latents] * 2).detach().clone().requires_grad_(True)
+        with torch.enable_grad():
+            model.unet(x_in, t, encoder_hidden_states=embeds_edit.detach())
+            loss = 0.0
+            for (_, m), ref in zip(cross, ref_maps[t]):
+                loss = loss + ((m.attn_probs.float() - ref.float()) ** 2).sum((1, 2)).mean(0)
+            grad, = torch.autograd.grad(loss, x_in)
+        with torch.no_grad():
+            x_new = (x_in - guidance_amount * grad).detach()   # torch.optim.SGD([x_in], lr=guidance_amount).step()
+            eps = runner(x_new, t, embeds_edit) if runner is not None else model.unet(x_new, t, encoder_hidden_states=embeds_edit)["sample"]
+            latents = x_new.chunk(2)[0]
+            latents = fused.step(eps, t, latents, guidance_scale)
+    if runner is not None:
+        runner.close()
+    return latents_rec, latents

@@ -65,6 +65,15 @@ class MyAttnProcessor:
     def _autograd_pass(attn, hidden_states, context, attention_mask):
         # out of scope for the forward-only kernels (needs d loss / d probs): differentiable torch arithmetic
         src = hidden_states if context is None else context
+        if context is None and hidden_states.is_cuda and attention_mask is None:
+            # self-attention maps are never read (sd_utils.py:108-110,169-171): a memory-efficient differentiable library
+            # attention instead of retaining N x N fp32 probabilities of every layer for the backward pass
+            h = attn.heads
+            q, k, v = attn.to_q(hidden_states), attn.to_k(src), attn.to_v(src)
+            q4, k4, v4 = (t.view(t.shape[0], t.shape[1], h, t.shape[2] // h).transpose(1, 2) for t in (q, k, v))
+            out = torch.nn.functional.scaled_dot_product_attention(q4, k4, v4, scale=attn.scale)
+            attn.attn_probs = None
+            return out.transpose(1, 2).reshape(q.shape[0], q.shape[1], -1)
         q = attn.head_to_batch_dim(attn.to_q(hidden_states))
         k = attn.head_to_batch_dim(attn.to_k(src))
         v = attn.head_to_batch_dim(attn.to_v(src))

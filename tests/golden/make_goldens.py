@@ -333,6 +333,57 @@ def gen_pix2pix_zero():
     _save("pix2pix_zero.pt", dict(prompts=prompts, latent_seed=4, pipe_seed=4, t=981, unet_out=out, layer_outputs=rec.records[0], cross_probs=probs, latent_hw=LAT))
 
 
+def gen_pix2pix_zero_loop():
+    """The two loops of pix2pix-zero/model/sd_utils.py:86-182 (map collection, then guidance gradient -> SGD step -> recomputed
+    noise -> DDIM step) restated around the REFERENCE's own MyAttnProcessor and the diffusers-style scheduler: the reference
+    driver itself needs diffusers' encode_prompt / prepare_latents, which are not installable here ("recomposed")."""
+    ref = load_reference("pix2pix-zero")
+    pipe = make_pipeline(tiny_config(), seed=4)
+    unet, _ = ref.attention_control.prep_unet(pipe.unet)
+    steps, guidance, lr = 3, 7.5, 0.1
+    pipe.scheduler.set_timesteps(steps)
+    emb_src = _context(pipe, ["a photo of a cat"])
+    emb_edit = _context(pipe, ["a photo of a dog"])
+    cross = [(n, m) for n, m in unet.named_modules() if type(m).__name__ == "Attention" and "attn2" in n]
+    lat0 = _latent(14, (1, 4, LAT, LAT))
+    latents = lat0.clone()
+    d_ref = {}
+    with torch.no_grad():
+        for t in pipe.scheduler.timesteps:
+            noise = unet(torch.cat([latents] * 2), t, encoder_hidden_states=emb_src).sample
+            d_ref[t.item()] = {n: m.attn_probs.detach().cpu() for n, m in cross}
+            nu, nc = noise.chunk(2)
+            latents = pipe.scheduler.step(nu + guidance * (nc - nu), t, latents)["prev_sample"]
+    rec = latents.clone()
+    latents = lat0.clone()
+    per_step = []
+    for t in pipe.scheduler.timesteps:
+        x_in = torch.cat([latents] * 2).detach().clone()
+        x_in.requires_grad = True
+        opt = torch.optim.SGD([x_in], lr=lr)
+        unet(x_in, t, encoder_hidden_states=emb_edit.detach())
+        loss = 0.0
+        for n, m in cross:
+            loss += ((m.attn_probs - d_ref[t.item()][n].detach()) ** 2).sum((1, 2)).mean(0)
+        loss.backward(retain_graph=False)
+        opt.step()
+        with torch.no_grad():
+            noise = unet(x_in.detach(), t, encoder_hidden_states=emb_edit).sample
+        latents = x_in.detach().chunk(2)[0]
+        nu, nc = noise.chunk(2)
+        latents = pipe.scheduler.step(nu + guidance * (nc - nu), t, latents)["prev_sample"]
+        per_step.append(latents.clone())
+    # without guidance (lr = 0) the edit loop is plain sampling with the edit prompt: shows how much the guidance moves the result
+    latents = lat0.clone()
+    with torch.no_grad():
+        for t in pipe.scheduler.timesteps:
+            noise = unet(torch.cat([latents] * 2), t, encoder_hidden_states=emb_edit).sample
+            nu, nc = noise.chunk(2)
+            latents = pipe.scheduler.step(nu + guidance * (nc - nu), t, latents)["prev_sample"]
+    _save("pix2pix_zero_loop.pt", dict(recomposed=True, steps=steps, guidance=guidance, guidance_amount=lr, latent_seed=14, pipe_seed=4, latent_hw=LAT,
+                                       prompts=["a photo of a cat", "a photo of a dog"], rec=rec, edit_per_step=per_step, edit_no_guidance=latents))
+
+
 def gen_oracle_pins():
     """Small known-answer vectors straight from the reference's controller METHODS on random tensors: they pin every
     function of oracle/controlled_attention.py without needing /root/reference at test time."""
@@ -417,6 +468,6 @@ def gen_ddim():
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["aligner", "oracle_pins", "ddim", "p2p", "masactrl", "pnp", "pnp_xl", "pix2pix_zero", "p2p_localblend", "masactrl_masks"]
+    which = sys.argv[1:] or ["aligner", "oracle_pins", "ddim", "p2p", "masactrl", "pnp", "pnp_xl", "pix2pix_zero", "p2p_localblend", "masactrl_masks", "pix2pix_zero_loop"]
     for w in which:
         globals()["gen_" + w]()

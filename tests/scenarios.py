@@ -165,6 +165,19 @@ def run_pix2pix_zero(g, device):
     return out.float().cpu(), rec.records[0], probs, (unet, originals)
 
 
+def run_pix2pix_zero_loop(g, device, guidance_amount=None, graphs=False):
+    pipe = make_pipeline(tiny_config(), seed=g["pipe_seed"], device=device)
+    unet, originals = pix2pix_zero.prep_unet(pipe.unet)
+    emb_src = editing.encode_prompts(pipe, g["prompts"][:1])
+    emb_edit = editing.encode_prompts(pipe, g["prompts"][1:])
+    hw = g["latent_hw"]
+    lat0 = latent(g["latent_seed"], (1, 4, hw, hw), device)
+    rec, edit = editing.pix2pix_zero_edit(pipe, emb_src, emb_edit, lat0, g["steps"], g["guidance"],
+                                          g["guidance_amount"] if guidance_amount is None else guidance_amount, graphs=graphs)
+    pix2pix_zero.restore_original_processors(unet, originals)
+    return rec.float().cpu(), edit.float().cpu()
+
+
 def run_p2p_localblend(g, device):
     cfg = UNetConfig(**g["config"])
     pipe = make_pipeline(cfg, seed=g["pipe_seed"], device=device)

@@ -389,3 +389,16 @@ def test_graph_replay_protocol_tracks_eager_counters(monkeypatch):
             assert (ed.cur_step, ed.cur_att_layer) == (shadow.cur_step, shadow.cur_att_layer)
     assert keys == [(False,), (False,), (True,), (True,), (True,)]
     assert masactrl.AttentionStore().graph_key() is None
+
+
+def test_pix2pix_zero_loops_reproduce_reference(monkeypatch):
+    """editing.pix2pix_zero_edit: map collection with the cache kept on the device, guidance gradient through the torch pass, SGD
+    step on the latents, recomputed noise, DDIM step — against the loops restated around the reference's own processor."""
+    cpu_backend.install(monkeypatch)
+    g = golden("pix2pix_zero_loop.pt")
+    rec, edit = scenarios.run_pix2pix_zero_loop(g, torch.device("cpu"))
+    assert torch.allclose(rec, g["rec"], atol=2e-4), (rec - g["rec"]).abs().max()
+    assert torch.allclose(edit, g["edit_per_step"][-1], atol=5e-4), (edit - g["edit_per_step"][-1]).abs().max()
+    # the guidance matters: without it the edit loop lands elsewhere
+    moved = (g["edit_no_guidance"] - g["edit_per_step"][-1]).abs().max()
+    assert moved > 20 * (edit - g["edit_per_step"][-1]).abs().max(), moved
