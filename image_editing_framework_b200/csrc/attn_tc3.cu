@@ -45,9 +45,13 @@ constexpr int ST = 3;
 constexpr int kTile = kTcChunkBytes;           // 16 KiB: one [128 x 64ch] box (head_dim <= 64)
 constexpr int kSmemOnes = 2 * 1024;            // [16 x 64] tile of 1.0 (K-major, SWIZZLE_128B footprint): B operand of the row-sum MMA
 constexpr int kSmemXchg = 8 * 1024;            // floats: row-max exchange [2 parities][2 streams][2 halves][128] | row sums [2][2][128] | split merge [2][128]
-#ifndef IEF_TC3_FINE_TRACE
-#define IEF_TC3_FINE_TRACE 0  // 1: extra clock64 stamps inside the pre-turn work (tools/tc3_trace.py prints them); costs ~2 %
+// clock64 phase stamps of CTA 0 for tools/tc3_trace.py: 0 = compiled out (the per-tile predicate tests alone cost ~5 % of the
+// softmax warps' instructions), 1 = per-tile phases, 2 = plus the sub-phases of the pre-turn work.
+// Build a traced library with IEF_EXTRA_NVCC_FLAGS="-DIEF_TC3_TRACE=2" csrc/build.sh
+#ifndef IEF_TC3_TRACE
+#define IEF_TC3_TRACE 0
 #endif
+#define IEF_TC3_FINE_TRACE (IEF_TC3_TRACE >= 2)
 #ifndef IEF_TC3_EMUL
 #define IEF_TC3_EMUL 0
 #endif
@@ -309,8 +313,13 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int vc = min(kBN, a.Nk - jj * kBN);
       float kn_cur = 0.f;  // requested here, needed after the score load: its latency hides behind the barrier wait and tcgen05.ld
       if constexpr (skip_guard) kn_cur = __ldg(a.knorm + ((int64_t)kb_tile * a.H + h) * a.knorm_tiles + jj);
+#if IEF_TC3_TRACE
       const bool trace = a.dbg != nullptr && lin == 0 && row == 0 && half == 0 && j < 64;
       long long* tr = trace ? a.dbg + (t * 64 + j) * 8 : nullptr;
+#else
+      constexpr bool trace = false;
+      long long* tr = nullptr;
+#endif
 #if IEF_TC3_FINE_TRACE
       long long* tr2 = trace ? a.dbg + 1024 + (t * 64 + j) * 4 : nullptr;  // sub-phases of the pre-turn work
 #endif
@@ -427,8 +436,10 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tc_fence_before();
       mbar_arrive(bar_p(t));
       if (trace) tr[5] = clock64();
-      acc0 = fadd2(acc0, acc1);
-      l += acc0.x + acc0.y;
+      if constexpr (!sum_mma) {
+        acc0 = fadd2(acc0, acc1);
+        l += acc0.x + acc0.y;
+      }
     }
     if (cta_trace && warp == 4 && lane == 0) a.dbg[1538] = clock64();
     if (my_nt > 0) {

@@ -109,11 +109,18 @@ __device__ __forceinline__ float2 exp2_fma(float2 t) {
 // EVERY = 0: plain. EVERY = n: every n-th column pair of a chunk is exponentiated here (before the turn), the others only scaled.
 template <int EVERY> __device__ __forceinline__ constexpr bool emul_pair(int pair) { return EVERY > 0 && (pair % (EVERY > 0 ? EVERY : 1)) == EVERY - 1; }
 
+#ifndef IEF_SCALAR_SCALE
+#define IEF_SCALAR_SCALE 0
+#endif
 template <int EVERY>
 __device__ __forceinline__ void scale_chunk_mix(uint32_t (&s)[32], float2 c2, float2 nmc) {
 #pragma unroll
   for (int i = 0; i < 32; i += 2) {
+#if IEF_SCALAR_SCALE
+    float2 x = make_float2(fmaf(__uint_as_float(s[i]), c2.x, nmc.x), fmaf(__uint_as_float(s[i + 1]), c2.x, nmc.x));
+#else
     float2 x = ffma2(make_float2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), c2, nmc);
+#endif
     if (emul_pair<EVERY>(i / 2)) x = exp2_fma(x);
     s[i] = __float_as_uint(x.x);
     s[i + 1] = __float_as_uint(x.y);

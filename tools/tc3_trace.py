@@ -1,5 +1,7 @@
 """Per-phase clock64 trace of CTA 0 of the generation-3 tcgen05 attention kernel (debug hook ief_debug_set_trace_buffer):
-one softmax thread (row 0, column half 0) of each stream stamps every tile."""
+one softmax thread (row 0, column half 0) of each stream stamps every tile.
+Needs a traced build:  IEF_EXTRA_NVCC_FLAGS="-DIEF_TC3_TRACE=2" bash image_editing_framework_b200/csrc/build.sh
+(the default library has the stamps compiled out)."""
 import ctypes as C
 import os
 import sys
@@ -20,6 +22,8 @@ ops.attention(q, k, v, H, d ** -0.5, impl=ops.IEF_IMPL_TCGEN05)
 torch.cuda.synchronize()
 lib.ief_debug_set_trace_buffer(None)
 t = buf.cpu()
+if int(t[:1024].abs().sum()) == 0:
+    sys.exit("no stamps recorded: rebuild the library with -DIEF_TC3_TRACE=2 (see the docstring)")
 sm = t[:1024].view(2, 64, 8)
 t0 = int(sm[0, 0, 0])
 nt = min(N // 128, 64)
