@@ -353,6 +353,9 @@ __global__ void __launch_bounds__(128) key_norm_kernel(const __nv_bfloat16* k, i
 // columns for the row-sum MMA, so the maximum pass is a larger share of the softmax instructions) and >= 24 key tiles (the
 // pre-pass launch costs 4-5 us): +3..7 %. At head_dim <= 48 and on short sequences it loses 3-13 %.
 static bool key_norm_prepass_pays(const ief_attn_params* p) {
+  static int force = -1;  // IEF_TC3_SKIPMAX=2: pre-pass wherever the kernel supports it (A/B runs)
+  if (force < 0) { const char* e = getenv("IEF_TC3_SKIPMAX"); force = (e && atoi(e) == 2) ? 1 : 0; }
+  if (force) return p->dtype == IEF_BF16 && p->d <= 64 && p->Nq >= 512 && p->key_bias == nullptr && p->probs_out == nullptr;
   return p->dtype == IEF_BF16 && p->d > 48 && p->d <= 64 && p->Nq >= 512 && ief_ceil_div(p->Nk, 128) * (p->k_src2 ? 2 : 1) >= 24 &&
          p->key_bias == nullptr && p->probs_out == nullptr;
 }
