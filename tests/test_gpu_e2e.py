@@ -253,3 +253,32 @@ def test_pix2pix_zero_loops_match_reference(cuda, graphs):
     # checked in fp32 by tests/test_host_logic.py::test_pix2pix_zero_loops_reproduce_reference on the same golden)
     db = psnr(edit, g["edit_per_step"][-1])
     assert db >= PSNR_DB, f"edit PSNR {db:.1f} dB"
+
+
+def test_fused_qkv_projection_matches_separate_linears(cuda, monkeypatch):
+    """hooks.project_qkv: one GEMM against the concatenated to_q/to_k/to_v (self) or to_k/to_v (cross) weights, q/k/v as strided
+    views consumed in place by the kernels; the cache follows in-place weight updates."""
+    from image_editing_framework_b200 import hooks, ops
+    from image_editing_framework_b200.standin import Attention
+    torch.manual_seed(0)
+    attn = Attention(query_dim=320, cross_attention_dim=768, heads=8, dim_head=40).to(cuda).to(torch.bfloat16)
+    self_attn = Attention(query_dim=320, heads=8, dim_head=40).to(cuda).to(torch.bfloat16)
+    x = torch.randn(2, 1024, 320, device=cuda, dtype=torch.bfloat16)
+    ctx = torch.randn(2, 77, 768, device=cuda, dtype=torch.bfloat16)
+    with torch.no_grad():
+        for module, context in ((self_attn, None), (attn, ctx)):
+            q, k, v = hooks.project_qkv(module, x, context)
+            assert not k.is_contiguous() and k.data_ptr() != v.data_ptr()      # views of one GEMM output
+            monkeypatch.setenv("IEF_FUSED_QKV", "0")
+            q0, k0, v0 = hooks.project_qkv(module, x, context)
+            monkeypatch.delenv("IEF_FUSED_QKV")
+            for a, b in ((q, q0), (k, k0), (v, v0)):
+                assert (a.float() - b.float()).abs().max().item() <= 2 ** -6 * b.float().abs().max().item()
+            fn = ops.attention if context is None else ops.cross_attention_edit
+            o, o0 = fn(q, k, v, 8, 40 ** -0.5), fn(q0, k0, v0, 8, 40 ** -0.5)
+            assert (o.float() - o0.float()).abs().max().item() < 2e-2
+        # in-place weight update invalidates the cached concatenation
+        k_before = hooks.project_qkv(self_attn, x, None)[1].clone()
+        self_attn.to_k.weight.mul_(2.0)
+        k_after = hooks.project_qkv(self_attn, x, None)[1]
+        assert (k_after.float() - 2 * k_before.float()).abs().max().item() <= 2 ** -6 * k_after.float().abs().max().item()
