@@ -79,6 +79,18 @@ def test_attn_fp16(cuda, impl):
     _check_attn(cuda, (2, 4, 512, 512, 64), impl, dtype=torch.float16)
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("shape", [
+    (2, 4, 512, 384, 16), (2, 2, 640, 640, 32), (1, 2, 600, 300, 8), (2, 2, 768, 768, 48), (2, 2, 768, 768, 56), (1, 8, 4096, 4096, 40),
+    (3, 2, 1024, 77, 40),
+])
+def test_attn_tcgen05_row_sum_mma_variants(cuda, shape, dtype):
+    """Generation 3b keeps the row sums in the 16 accumulator columns after O when head_dim <= 48 (column offset 16 / 32 / 48 for
+    head dims 8-16 / 17-32 / 33-48, ones tile in the kernel's dtype); head_dim 56 and 64 take the variant with register sums.
+    Both launch flavours (256-row pair CTAs, split-KV CTAs) are hit: small grids go split, B=1 x 8 heads x 4096 goes pair."""
+    _check_attn(cuda, shape, ops.IEF_IMPL_TCGEN05, dtype=dtype, seed=5)
+
+
 @pytest.mark.parametrize("impl", [ops.IEF_IMPL_MMA, ops.IEF_IMPL_TCGEN05])
 @pytest.mark.parametrize("name,src", [
     ("p2p_self_replace", dict(q_src=[0, 1, 2, 2], k_src=[0, 1, 2, 2])),
