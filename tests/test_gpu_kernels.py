@@ -119,6 +119,15 @@ def test_attn_large_logits_lazy_rescale(cuda):
     want = orc.indexed_attention(q, k, v, H, d ** -0.5)
     got = ops.attention(q.to(cuda), k.to(cuda), v.to(cuda), H, d ** -0.5, impl=ops.IEF_IMPL_TCGEN05)
     assert (got.float().cpu() - want).abs().max().item() < TOL
+    # head_dim 40: the row sums live in the accumulator (row-sum MMA) and must be rescaled together with O; keys sorted so that
+    # the row maxima keep growing from tile to tile
+    for dt in (torch.bfloat16, torch.float16):
+        q, k, v = _qkv(1, 640, 2048, 2, 40, 6, dtype=dt, spread=3.0)
+        order = (k.float()[0] @ q.float()[0].mean(0)).argsort()
+        k, v = k[:, order].contiguous(), v[:, order].contiguous()
+        want = orc.indexed_attention(q, k, v, 2, 40 ** -0.5)
+        got = ops.attention(q.to(cuda), k.to(cuda), v.to(cuda), 2, 40 ** -0.5, impl=ops.IEF_IMPL_TCGEN05)
+        assert (got.float().cpu() - want).abs().max().item() < TOL
 
 
 @pytest.mark.parametrize("case", ["plain", "late_large_keys", "huge_norms", "union"])
