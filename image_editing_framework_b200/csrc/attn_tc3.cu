@@ -52,6 +52,9 @@ constexpr int kSmemXchg = 8 * 1024;            // floats: row-max exchange [2 pa
 #define IEF_TC3_TRACE 0
 #endif
 #define IEF_TC3_FINE_TRACE (IEF_TC3_TRACE >= 2)
+#ifndef IEF_TC3_HANDOVER_LATE
+#define IEF_TC3_HANDOVER_LATE 0  // experiment: hand the turn over after the whole exp section instead of one chunk early
+#endif
 #ifndef IEF_TC3_EMUL
 #define IEF_TC3_EMUL 0
 #endif
@@ -427,10 +430,16 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       uint32_t u[16];
       if constexpr (sum_mma) exp_pack_chunk_nosum<E, EMUL>(s0, u); else exp_pack_chunk_mix<E, EMUL>(s0, u, acc0, acc1);
       tmem_st16(tP, u);
+#if !IEF_TC3_HANDOVER_LATE
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_x(t ^ 1));  // hand the MUFU over one chunk early
+#endif
       if constexpr (sum_mma) exp_pack_chunk_nosum<E, EMUL>(s1, u); else exp_pack_chunk_mix<E, EMUL>(s1, u, acc0, acc1);
       tmem_st16(tP + 16, u);
+#if IEF_TC3_HANDOVER_LATE
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_x(t ^ 1));
+#endif
       if (trace) tr[4] = clock64();
       tc_wait_st();
       tc_fence_before();

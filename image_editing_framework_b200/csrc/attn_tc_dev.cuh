@@ -139,10 +139,10 @@ __device__ __forceinline__ void exp_pack_chunk_mix(const uint32_t (&s)[32], uint
 }
 
 // the same without the row sum (it is computed by the tensor pipe: P x ones)
-template <typename E, int EVERY>
+template <typename E, int EVERY, int BEGIN = 0, int END = 16>
 __device__ __forceinline__ void exp_pack_chunk_nosum(const uint32_t (&s)[32], uint32_t (&u)[16]) {
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
+  for (int i = BEGIN; i < END; ++i) {
     float2 x = make_float2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1]));
     if (!emul_pair<EVERY>(i)) { x.x = ief_exp2(x.x); x.y = ief_exp2(x.y); }
     u[i] = E::pack(x.x, x.y);
