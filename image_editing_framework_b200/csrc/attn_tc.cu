@@ -277,11 +277,11 @@ EncodeTiledFn get_encode() {
 // TMA dimension i+1. Box = 64 channels x 128 tokens, SWIZZLE_128B, out-of-bounds reads return zero —
 // that is how head_dim 40/80/160 is padded to the 64-element swizzle atom and how ragged token counts
 // are padded to the 128-row tile.
-int make_map(CUtensorMap* m, int dtype, const ief_tensor4& t, int d, int N, int H, int B, int32_t perm[3]) {
+int make_map(CUtensorMap* m, int dtype, const ief_tensor4& t, int d, int N, int H, int B, int32_t perm[3], int box_rows = kBN) {
   EncodeTiledFn enc = get_encode();
   IEF_REQUIRE(enc != nullptr, IEF_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   struct Dim { int kind; uint64_t size; int64_t stride; uint32_t box; } dims[3] = {
-      {0, (uint64_t)N, t.stride_n, (uint32_t)kBN}, {1, (uint64_t)H, t.stride_h, 1u}, {2, (uint64_t)B, t.stride_b, 1u}};
+      {0, (uint64_t)N, t.stride_n, (uint32_t)box_rows}, {1, (uint64_t)H, t.stride_h, 1u}, {2, (uint64_t)B, t.stride_b, 1u}};
   // size-1 dimensions may carry arbitrary strides: sort them outermost and synthesise a legal stride below
   for (auto& x : dims) if (x.size == 1) x.stride = INT64_MAX / 4;
   for (int i = 0; i < 3; ++i)
@@ -321,6 +321,10 @@ int launch_tc(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& m
 }
 
 }  // namespace
+
+int ief_tc_make_map(CUtensorMap* m, int dtype, const ief_tensor4& t, int d, int N, int H, int B, int32_t perm[3], int box_rows) {
+  return make_map(m, dtype, t, d, N, H, B, perm, box_rows);
+}
 
 // max_j |k_j| per 128-key tile of every (row, head), inflated by 0.1 %: with |q_i| it bounds the tile's scores (Cauchy-Schwarz),
 // which lets attn_tc3 (bf16) skip the running-maximum pass on most tiles. One thread per key, 16-byte loads.

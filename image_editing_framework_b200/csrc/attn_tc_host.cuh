@@ -33,6 +33,8 @@ __device__ __forceinline__ void tc_tma_tile(uint32_t dst, const CUtensorMap* m, 
 }
 
 long long* ief_debug_trace_buffer();
+// 4-D SWIZZLE_128B tensor map over a [rows, tokens, heads, d] view, box = 64 channels x box_rows tokens (attn_tc.cu)
+int ief_tc_make_map(CUtensorMap* m, int dtype, const ief_tensor4& t, int d, int N, int H, int B, int32_t perm[3], int box_rows);
 int ief_attn_tc3_launch(const ief_attn_params* p, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const TcArgs& a, int mode,
                         cudaStream_t st);  // mode: 0 pair, 1 split, 2 hybrid (full waves as pairs, remainder split)
 int ief_attn_tc2s_launch(const ief_attn_params* p, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const TcArgs& a, cudaStream_t st);

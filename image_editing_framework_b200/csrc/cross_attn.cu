@@ -18,6 +18,9 @@
 #include "mma_utils.cuh"
 #include <math.h>
 
+bool ief_cross_tc_supported(const ief_cross_params* p);
+int ief_cross_tc_launch(const ief_cross_params* p, cudaStream_t st);
+
 using namespace mmau;
 
 namespace {
@@ -334,7 +337,9 @@ extern "C" int ief_cross_attn_edit_fwd(const ief_cross_params* p, void* stream) 
                 "ief_cross_attn_edit_fwd: mapper_idx and refine_alpha required for REFINE");
     flavour = (p->mode == IEF_EDIT_REPLACE && !(p->mapper_nz_idx && p->mapper_nz_w)) ? kEditDense : kEditGather;
   }
-  dim3 grid(ief_ceil_div(p->Nq, kBM), p->H, p->B);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // un-edited rows without a map output: the tcgen05 kernel (cross_tc.cu), a row per thread instead of a row per quad
+  if (flavour == kPlain && p->probs_out == nullptr && ief_cross_tc_supported(p)) return ief_cross_tc_launch(p, st);
+  dim3 grid(ief_ceil_div(p->Nq, kBM), p->H, p->B);
   return p->dtype == IEF_BF16 ? launch_flavour<IEF_BF16>(a, flavour, grid, st) : launch_flavour<IEF_F16>(a, flavour, grid, st);
 }
