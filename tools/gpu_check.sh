@@ -13,7 +13,12 @@ IEF_TC_SPLITKV=2 run tc_v3_hybrid "tcgen05 or fp16 or row_sources or masactrl or
 IEF_TC_SPLITKV=0 run tc_v3_pair "tcgen05 or fp16 or row_sources or masactrl or lazy or strided"
 IEF_TC_VERSION=2 IEF_TC_SPLITKV=1 run tc_v2_split "tcgen05 or fp16 or row_sources or masactrl or lazy or strided"
 IEF_TC_VERSION=1 run tc_v1 "tcgen05 or fp16 or row_sources or masactrl or lazy or strided"
+IEF_TC3_NO_SUM_MMA=1 run tc_v3_no_summma "tcgen05 or fp16 or row_sources or masactrl or lazy or strided"
+IEF_TC3_SKIPMAX=2 run tc_v3_skip_everywhere "tcgen05 or fp16 or row_sources or masactrl or lazy or strided"
+IEF_TC3_SKIPMAX=0 run tc_v3_no_skip "tcgen05 or fp16 or row_sources or masactrl or lazy or strided"
 run cross "cross_attention"
+IEF_CROSS_TC=0 run cross_mma_only "cross_attention"
+run masked "key_bias or mask_blend"
 run elem "ddim or accumulate or local_blend"
 echo "=== e2e"; timeout 900 python -m pytest tests/test_gpu_e2e.py -q -m gpu -p no:cacheprovider --timeout=600 > gpurun_out/t_e2e.log 2>&1; echo "exit $?"; tail -25 gpurun_out/t_e2e.log
 echo "=== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "exit $?"; tail -3 gpurun_out/smoke.log
