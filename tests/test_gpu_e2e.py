@@ -282,3 +282,20 @@ def test_fused_qkv_projection_matches_separate_linears(cuda, monkeypatch):
         self_attn.to_k.weight.mul_(2.0)
         k_after = hooks.project_qkv(self_attn, x, None)[1]
         assert (k_after.float() - 2 * k_before.float()).abs().max().item() <= 2 ** -6 * k_after.float().abs().max().item()
+
+
+def test_graph_runner_falls_back_to_eager_for_unreplayable_controllers(cuda):
+    """masactrl.AttentionStore keeps per-step python lists of fresh tensors: graph_key() is None and every forward runs eagerly."""
+    from image_editing_framework_b200 import masactrl, editing
+    from image_editing_framework_b200.standin import make_pipeline, tiny_config
+    prompts = ["a photo of a sitting cat", "a photo of a running cat"]
+    outs, stats = [], {}
+    for graphs in (False, True):
+        pipe = make_pipeline(tiny_config(), seed=3, device=cuda)
+        ed = masactrl.AttentionStore(res=[16], min_step=0, max_step=10)
+        masactrl.regiter_attention_editor_diffusers(pipe, ed)
+        lat = scenarios.latent(5, (1, 4, 16, 16), cuda)
+        outs.append(editing.masactrl_edit(pipe, prompts, torch.cat([lat, lat]), 4, 7.5, graphs=graphs, editor=ed, stats=stats).float().cpu())
+        assert ed.cur_step == 4 and ed.valid_steps == 4 and len(ed.self_attns) > 0
+    assert stats["replays"] == 0 and stats["eager_calls"] == 4
+    assert psnr(outs[1], outs[0]) >= 60.0

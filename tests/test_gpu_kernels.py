@@ -408,3 +408,44 @@ def test_full_size_properties(cuda, name, B, H, N, d):
     rows = slice(N - 130, N)
     want = orc.indexed_attention(q[:, rows].cpu(), k.cpu(), v.cpu(), H, scale, k_src=src, v_src=src)
     assert (out[:, rows].float().cpu() - want).abs().max().item() < TOL
+
+
+def test_attn_workspace_contract(cuda):
+    """ief_attn_workspace_bytes: non-zero only where the key-norm pre-pass pays (bf16, head_dim 49-64, >= 24 key tiles); a call
+    without workspace, with too small a workspace, or with the pre-pass gives the same softmax."""
+    import ctypes as C
+    B, H, N, d = 1, 2, 3200, 64
+    q, k, v = (t.to(cuda) for t in _qkv(B, N, N, H, d, 41))
+    out = torch.empty_like(q)
+
+    def params(qq, kk, vv, dd):
+        p = _cabi.AttnParams()
+        q4, k4, v4, o4 = (ops._as4(t, H) for t in (qq, kk, vv, out if dd == d else torch.empty_like(qq)))
+        p.q, p.k, p.v, p.o = (ops._t4(t, H) for t in (q4, k4, v4, o4))
+        p.dtype = _cabi.IEF_BF16 if qq.dtype == torch.bfloat16 else _cabi.IEF_F16
+        p.B, p.H, p.Nq, p.Nk, p.d = qq.shape[0], H, qq.shape[1], kk.shape[1], dd
+        p.scale, p.impl = dd ** -0.5, _cabi.IEF_IMPL_TCGEN05
+        return p
+
+    lib = _cabi.lib()
+    p = params(q, k, v, d)
+    need = lib.ief_attn_workspace_bytes(C.byref(p))
+    assert need == B * H * 25 * 4
+    q40 = q[..., :H * 40].contiguous()
+    assert lib.ief_attn_workspace_bytes(C.byref(params(q40, q40, q40, 40))) == 0            # head_dim 40: row-sum MMA variant instead
+    assert lib.ief_attn_workspace_bytes(C.byref(params(q[:, :1024], k[:, :1024], v[:, :1024], d))) == 0   # 8 key tiles: too short
+    qh = q.to(torch.float16)
+    assert lib.ief_attn_workspace_bytes(C.byref(params(qh, qh, qh, d))) == 0                # fp16 keeps the exact maximum
+    stream = torch.cuda.current_stream().cuda_stream
+    results = []
+    for ws_bytes in (0, need // 2, need):
+        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=cuda)
+        p.workspace, p.workspace_bytes = (ws.data_ptr(), ws_bytes) if ws_bytes else (None, 0)
+        out.zero_()
+        _cabi.check("ief_attn_fwd", lib.ief_attn_fwd(C.byref(p), stream))
+        torch.cuda.synchronize()
+        results.append(out.float().cpu().clone())
+    want = orc.indexed_attention(q.cpu(), k.cpu(), v.cpu(), H, d ** -0.5)
+    for r in results:
+        assert (r - want).abs().max().item() < TOL
+    assert torch.equal(results[0], results[1])          # too small a workspace is ignored: identical launches
