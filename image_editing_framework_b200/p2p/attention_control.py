@@ -1,7 +1,16 @@
-"""AttentionReplace / AttentionRefine / AttentionReweight with the constructor signatures of
-p2p/model/attention_control.py:8-46. Each class only prepares device tables; the arithmetic of
-`replace_cross_attention` (einsum with the 77x77 mapper :16, gather + alpha blend :29-30, equaliser :45)
-runs inside ief_cross_attn_edit_fwd.
+"""The three Prompt-to-Prompt edit controllers, constructor-compatible with p2p/model/attention_control.py:8-46.
+
+In the reference each class overrides `replace_cross_attention(attn_base, att_replace)`, which transforms a materialised
+[heads, pixels, 77] probability tensor:
+
+    AttentionReplace   einsum('hpw,bwn->bhpn', base, mapper)                        (:15-16)
+    AttentionRefine    base[:, :, mapper] * alphas + replace * (1 - alphas)        (:28-31)
+    AttentionReweight  (previous controller's edit, if any) * equalizer             (:42-46)
+
+Here no such tensor exists. A controller only owns the small device tables of its edit and describes them to the fused
+cross-attention kernel through `cross_edit()`; ief_cross_attn_edit_fwd applies the edit to the probabilities while they are
+still in registers (csrc/cross_attn.cu). Public attributes the reference exposes (`mapper`, `alphas`, `equalizer`,
+`prev_controller`) keep their names, shapes and dtypes.
 """
 from __future__ import annotations
 
@@ -14,49 +23,100 @@ from . import seq_aligner
 from .attention_base import AttentionControlEdit
 from .ptp_utils import LocalBlend
 
+_CUDA0 = torch.device("cuda:0")
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    return t.to(torch.float32).contiguous()
+
+
+def _expect(table: torch.Tensor, shape, what: str) -> torch.Tensor:
+    """The kernel indexes these tables with (edit slot, token): a mis-shaped one must fail here, not read out of bounds there."""
+    if tuple(table.shape) != tuple(shape):
+        raise ValueError(f"{what}: expected shape {tuple(shape)}, got {tuple(table.shape)} — one row per target prompt, "
+                         "tokenizer.model_max_length tokens")
+    return table
+
 
 class AttentionReplace(AttentionControlEdit):
+    """Word swap: the target prompt's probabilities become the source prompt's, routed through the [77, 77] token mapper."""
 
-    def __init__(self, prompts, tokenizer, num_steps: int, cross_replace_steps: float, self_replace_steps: float,
-                 local_blend: Optional[LocalBlend] = None, device=torch.device("cuda:0"), LOW_RESOURCE=False, dtype=torch.float32):
-        super().__init__(prompts, tokenizer, num_steps, cross_replace_steps, self_replace_steps, local_blend, device, LOW_RESOURCE)
-        self.mapper = seq_aligner.get_replacement_mapper(prompts, tokenizer).to(device).to(dtype)
+    def __init__(
+        self,
+        prompts,
+        tokenizer,
+        num_steps: int,
+        cross_replace_steps: float,
+        self_replace_steps: float,
+        local_blend: Optional[LocalBlend] = None,
+        device=_CUDA0,
+        LOW_RESOURCE=False,
+        dtype=torch.float32,
+    ):
+        AttentionControlEdit.__init__(self, prompts, tokenizer, num_steps, cross_replace_steps, self_replace_steps, local_blend, device, LOW_RESOURCE)
+        aligned = seq_aligner.get_replacement_mapper(prompts, tokenizer)     # [targets, 77, 77], rows sum to 1
+        tokens = aligned.shape[-1]
+        self.mapper = _expect(aligned, (len(prompts) - 1, tokens, tokens), "replacement mapper").to(device).to(dtype)
 
     def cross_edit(self) -> ops.CrossEdit:
-        return ops.CrossEdit(ops.IEF_EDIT_REPLACE, self.mapper.shape[0], mapper=self.mapper.to(torch.float32).contiguous())
+        # CrossEdit derives the sparse (<= 8 source tokens per target token) form the kernel prefers from the dense mapper
+        return ops.CrossEdit(ops.IEF_EDIT_REPLACE, self.mapper.shape[0], mapper=_f32(self.mapper))
 
 
 class AttentionRefine(AttentionControlEdit):
+    """Prompt refinement: target tokens aligned to a source token take its probability (gather), new tokens keep their own."""
 
-    def __init__(self, prompts, tokenizer, num_steps: int, cross_replace_steps: float, self_replace_steps: float,
-                 local_blend: Optional[LocalBlend] = None, device=torch.device("cuda:0"), LOW_RESOURCE=False):
-        super().__init__(prompts, tokenizer, num_steps, cross_replace_steps, self_replace_steps, local_blend, device, LOW_RESOURCE)
-        mapper, alphas = seq_aligner.get_refinement_mapper(prompts, tokenizer)
-        self.mapper, alphas = mapper.to(device), alphas.to(device)
-        self.alphas = alphas.reshape(alphas.shape[0], 1, 1, alphas.shape[1])
+    def __init__(
+        self,
+        prompts,
+        tokenizer,
+        num_steps: int,
+        cross_replace_steps: float,
+        self_replace_steps: float,
+        local_blend: Optional[LocalBlend] = None,
+        device=_CUDA0,
+        LOW_RESOURCE=False,
+    ):
+        AttentionControlEdit.__init__(self, prompts, tokenizer, num_steps, cross_replace_steps, self_replace_steps, local_blend, device, LOW_RESOURCE)
+        gather_idx, keep = seq_aligner.get_refinement_mapper(prompts, tokenizer)   # int64 [targets, 77] (may hold -1), 0/1 [targets, 77]
+        _expect(keep, gather_idx.shape, "refinement alphas")
+        if int(gather_idx.min()) < -1 or int(gather_idx.max()) >= gather_idx.shape[-1]:
+            raise ValueError("refinement mapper holds token positions outside [-1, max_length)")
+        keep = keep.to(device)
+        self.mapper = _expect(gather_idx, (len(prompts) - 1, gather_idx.shape[-1]), "refinement mapper").to(device)
+        self.alphas = keep.reshape(keep.shape[0], 1, 1, keep.shape[1])
 
     def cross_edit(self) -> ops.CrossEdit:
-        n = self.mapper.shape[0]
-        return ops.CrossEdit(ops.IEF_EDIT_REFINE, n, mapper_idx=self.mapper.to(torch.int32).contiguous(),
-                             refine_alpha=self.alphas.reshape(n, -1).to(torch.float32).contiguous())
+        targets = self.mapper.shape[0]
+        return ops.CrossEdit(ops.IEF_EDIT_REFINE, targets, mapper_idx=self.mapper.to(torch.int32).contiguous(),
+                             refine_alpha=_f32(self.alphas.reshape(targets, -1)))
 
 
 class AttentionReweight(AttentionControlEdit):
+    """Per-token re-weighting with an equalizer, optionally on top of another controller's edit."""
 
-    def __init__(self, prompts, tokenizer, num_steps: int, cross_replace_steps: float, self_replace_steps: float, equalizer,
-                 local_blend: Optional[LocalBlend] = None, controller: Optional[AttentionControlEdit] = None,
-                 device=torch.device("cuda:0"), LOW_RESOURCE=False, dtype=torch.float32):
-        super().__init__(prompts, tokenizer, num_steps, cross_replace_steps, self_replace_steps, local_blend, device, LOW_RESOURCE)
-        self.equalizer = equalizer.to(device).to(dtype)
+    def __init__(
+        self,
+        prompts,
+        tokenizer,
+        num_steps: int,
+        cross_replace_steps: float,
+        self_replace_steps: float,
+        equalizer,
+        local_blend: Optional[LocalBlend] = None,
+        controller: Optional[AttentionControlEdit] = None,
+        device=_CUDA0,
+        LOW_RESOURCE=False,
+        dtype=torch.float32,
+    ):
+        AttentionControlEdit.__init__(self, prompts, tokenizer, num_steps, cross_replace_steps, self_replace_steps, local_blend, device, LOW_RESOURCE)
         self.prev_controller = controller
+        self.equalizer = equalizer.to(device).to(dtype)
 
     def cross_edit(self) -> ops.CrossEdit:
-        n = self.batch_size - 1
-        if self.equalizer.shape[0] != n:
-            raise ValueError(f"equalizer has {self.equalizer.shape[0]} rows but there are {n} target prompts")
-        if self.prev_controller is not None:
-            e = self.prev_controller.cross_edit()
-        else:
-            e = ops.CrossEdit(ops.IEF_EDIT_NONE, n)
-        return ops.CrossEdit(e.mode, n, mapper=e.mapper, mapper_idx=e.mapper_idx, refine_alpha=e.refine_alpha,
-                             equalizer=self.equalizer.to(torch.float32).contiguous(), mapper_nz_idx=e.mapper_nz_idx, mapper_nz_w=e.mapper_nz_w)
+        targets = self.batch_size - 1
+        if self.equalizer.shape[0] != targets:
+            raise ValueError(f"equalizer has {self.equalizer.shape[0]} rows but there are {targets} target prompts")
+        inner = self.prev_controller.cross_edit() if self.prev_controller is not None else ops.CrossEdit(ops.IEF_EDIT_NONE, targets)
+        return ops.CrossEdit(inner.mode, targets, mapper=inner.mapper, mapper_idx=inner.mapper_idx, refine_alpha=inner.refine_alpha,
+                             equalizer=_f32(self.equalizer), mapper_nz_idx=inner.mapper_nz_idx, mapper_nz_w=inner.mapper_nz_w)
