@@ -32,6 +32,12 @@
 
 using namespace sm100;
 
+// clock64 phase stamps for tools/tc2_trace.py are compiled out by default (their per-tile predicate tests cost ~3 %):
+// rebuild with IEF_EXTRA_NVCC_FLAGS="-DIEF_TC2_TRACE=1" to get them back
+#ifndef IEF_TC2_TRACE
+#define IEF_TC2_TRACE 0
+#endif
+
 namespace {
 
 constexpr int kBM = 128;                 // rows per query tile (two tiles per CTA)
@@ -179,7 +185,11 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int s = j % ST, ph = (j / ST) & 1;
       const int s1 = (j + 1) % ST, ph1 = ((j + 1) / ST) & 1;
       const bool more = j + 1 < nt;
+#if IEF_TC2_TRACE
       const bool trace = a.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j < 64;
+#else
+      constexpr bool trace = false;
+#endif
       if constexpr (Cfg::kSplitP) {
         // next score tiles first: they only need S_t(j) to be in the softmax registers
         if (more) {
@@ -249,8 +259,13 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const bool blk2 = j >= a.nt1;
       const int jj = blk2 ? j - a.nt1 : j;
       const int vc = min(kBN, a.Nk - jj * kBN);
+#if IEF_TC2_TRACE
       const bool trace = a.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && row == 0 && j < 64;
       long long* tr = trace ? a.dbg + (t * 64 + j) * 8 : nullptr;
+#else
+      constexpr bool trace = false;
+      long long* tr = nullptr;
+#endif
       if (trace) tr[0] = clock64();
       mbar_wait(bar_s(t), j & 1);
       tc_fence_after();

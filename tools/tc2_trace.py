@@ -1,4 +1,6 @@
-"""Per-phase clock64 trace of CTA (0,0,0) of the v2 tcgen05 attention kernel (debug hook ief_debug_set_trace_buffer)."""
+"""Per-phase clock64 trace of CTA (0,0,0) of the v2 tcgen05 attention kernel (debug hook ief_debug_set_trace_buffer).
+Needs a traced build: IEF_EXTRA_NVCC_FLAGS="-DIEF_TC2_TRACE=1" bash image_editing_framework_b200/csrc/build.sh, and
+IEF_TC_VERSION=2 to select the generation-2 kernel for head_dim <= 64."""
 import ctypes as C
 import os
 import sys
