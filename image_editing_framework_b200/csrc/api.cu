@@ -76,9 +76,10 @@ extern "C" int ief_attn_fwd(const ief_attn_params* p, void* stream) {
     impl = IEF_IMPL_MMA;
   }
   if (any_bias) {
-    IEF_REQUIRE(impl != IEF_IMPL_TCGEN05, IEF_ERR_UNSUPPORTED, "ief_attn_fwd: key_bias is only implemented by the mma kernel");
     IEF_REQUIRE(p->k_src2 == nullptr, IEF_ERR_UNSUPPORTED, "ief_attn_fwd: key_bias cannot be combined with a second key/value block");
-    impl = IEF_IMPL_MMA;
+    IEF_REQUIRE(impl != IEF_IMPL_TCGEN05 || p->d <= 64, IEF_ERR_UNSUPPORTED,
+                "ief_attn_fwd: key_bias on the tcgen05 kernel needs head_dim <= 64 (got %d)", p->d);
+    if (p->d > 64) impl = IEF_IMPL_MMA;
   }
   if (impl == IEF_IMPL_AUTO) {
     // the tcgen05 kernel pays off once a head has at least a few 128-key tiles; tiny layers

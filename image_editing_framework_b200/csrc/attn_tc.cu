@@ -374,6 +374,7 @@ bool ief_attn_tc_supported(const ief_attn_params* p, const char** why) {
   if (why) *why = w;
 #define NO(msg) do { if (why) *why = msg; return false; } while (0)
   if (p->probs_out) NO("probs_out requires the mma two-sweep kernel");
+  if (p->key_bias && p->bias_sel && (p->d > 64 || p->k_src2)) NO("key_bias: only the head_dim <= 64 generation of the tcgen05 kernel takes it, and no second key block");
   if (p->dtype != IEF_BF16 && p->dtype != IEF_F16) NO("dtype must be bf16 or f16");
   if (p->d % 8 != 0 || p->d < 8 || p->d > 192) NO("head_dim must be a multiple of 8 in [8,192]");
   if (p->Nq < 1 || p->Nk < 1) NO("empty sequence");
@@ -410,6 +411,9 @@ int ief_attn_tc_launch(const ief_attn_params* p, const IefRowTable& rows, cudaSt
   a.idesc_sum = make_idesc_f16(kBM, 16, fmt, 0, 0);
   a.knorm = nullptr;
   a.knorm_tiles = 0;
+  a.key_bias = nullptr;
+  for (int i = 0; i < p->B; ++i)
+    if (rows.bias[i] >= 0) a.key_bias = p->key_bias;
   a.sum_mma = (a.dv_mma <= 48 && getenv("IEF_TC3_NO_SUM_MMA") == nullptr) ? 1 : 0;
   a.scale_log2 = p->scale * kLog2e;
   a.rows = rows;

@@ -76,7 +76,7 @@ __device__ __forceinline__ float approx_sqrt(float x) { float y; asm("sqrt.appro
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
-template <int DTYPE, bool SPLIT, int EMUL, bool SUMMMA, bool SKIP>
+template <int DTYPE, bool SPLIT, int EMUL, bool SUMMMA, bool SKIP, bool BIAS>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                 const __grid_constant__ TcArgs a) {
@@ -280,7 +280,11 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t tS = tmem_base + 128 * t + 64 * half + lane_off;
     const uint32_t tP = tmem_base + 256 + 64 * t + 32 * half + lane_off;
     const uint32_t tO = tmem_base + 384 + 64 * t + lane_off;
-    const float c2 = a.scale_log2;
+    // BIAS variant, rows with a key bias: the scores are turned into t = s * scale_log2 + bias * log2(e) right after the load, so the
+    // maximum sees the bias and everything downstream works with a unit scale
+    const float* bias_row = nullptr;
+    if constexpr (BIAS) bias_row = a.rows.bias[b] >= 0 ? a.key_bias + (int64_t)a.rows.bias[b] * a.Nk : nullptr;
+    const float c2 = (BIAS && bias_row != nullptr) ? 1.f : a.scale_log2;
     float m_used = -INFINITY, l = 0.f;
     float qn_max = INFINITY, m_floor = -INFINITY;  // stream-wide max |q_row| and min first-tile row maximum (scaled): the skip test
     float qn_row = 0.f;
@@ -338,6 +342,21 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_c(t));  // S_t(j) is in registers: the tensor pipe may overwrite it with S_t(j+1)
       if (trace) tr[2] = clock64();
+      if constexpr (BIAS) {
+        if (bias_row != nullptr) {
+          // masked keys carry finfo.min in the reference; clamped so that the product with log2(e) stays finite and a row whose keys
+          // are all masked still comes out as the uniform average, as it does there. Out-of-range columns are masked below.
+          const float* bp = bias_row + jj * kBN + 64 * half;
+          const float sl = a.scale_log2;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float b0 = 64 * half + i < vc ? fmaxf(__ldg(bp + i) * 1.4426950408889634f, -3.0e38f) : 0.f;
+            const float b1 = 64 * half + 32 + i < vc ? fmaxf(__ldg(bp + 32 + i) * 1.4426950408889634f, -3.0e38f) : 0.f;
+            s0[i] = __float_as_uint(fmaf(__uint_as_float(s0[i]), sl, b0));
+            s1[i] = __float_as_uint(fmaf(__uint_as_float(s1[i]), sl, b1));
+          }
+        }
+      }
       if (vc < kBN) {
         mask_chunk(s0, 64 * half, vc);
         mask_chunk(s1, 64 * half + 32, vc);
@@ -532,9 +551,9 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (cta_trace && threadIdx.x == 32) a.dbg[1541] = clock64();
 }
 
-template <int DTYPE, bool SPLIT, bool SUMMMA, bool SKIP>
+template <int DTYPE, bool SPLIT, bool SUMMMA, bool SKIP, bool BIAS = false>
 int launch_tc3s(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, TcArgs a, int first, int count, int nq_blocks, cudaStream_t st) {
-  auto kern = attn_tc3_kernel<DTYPE, SPLIT, kDefaultEmul, SUMMMA, SKIP>;
+  auto kern = attn_tc3_kernel<DTYPE, SPLIT, kDefaultEmul, SUMMMA, SKIP, BIAS>;
   static bool configured = false;
   if (!configured) {
     IEF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg3<SPLIT>::kSmemBytes));
@@ -550,6 +569,9 @@ int launch_tc3s(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap&
 
 template <int DTYPE, bool SPLIT>
 int launch_tc3(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, TcArgs a, int first, int count, int nq_blocks, cudaStream_t st) {
+  if (a.key_bias != nullptr)  // masked MasaCtrl passes: the variant that adds a per-key bias before the maximum
+    return a.sum_mma ? launch_tc3s<DTYPE, SPLIT, true, false, true>(mq, mk, mv, a, first, count, nq_blocks, st)
+                     : launch_tc3s<DTYPE, SPLIT, false, false, true>(mq, mk, mv, a, first, count, nq_blocks, st);
   if constexpr (DTYPE == IEF_BF16) {
     if (a.knorm != nullptr)  // key-norm pre-pass available: the variant that skips provably harmless row-maximum passes
       return a.sum_mma ? launch_tc3s<DTYPE, SPLIT, true, true>(mq, mk, mv, a, first, count, nq_blocks, st)

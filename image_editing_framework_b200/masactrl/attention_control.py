@@ -98,7 +98,7 @@ class _MaskedMutualMixin:
     only and background keys only (two softmaxes) — and are blended per query position with the target mask
     (MutualSelfAttentionControlMask.forward :152-181, MaskAuto.forward :271-326).
 
-    Three ief_attn_fwd launches (source rows; fg pass; bg pass — the biased passes on the mma kernel) + one ief_mask_blend;
+    Three ief_attn_fwd launches (source rows; fg pass; bg pass) + one ief_mask_blend;
     the reference materialises [2h, N, N] scores and probabilities per target row instead."""
 
     def _masked_forward(self, q, k, v, num_heads, scale, key_bias: torch.Tensor, spatial_w: torch.Tensor) -> torch.Tensor:

@@ -90,7 +90,8 @@ typedef struct ief_attn_params {
   const float* key_bias;   /* device fp32 [n_bias, Nk] or NULL: additive per-key bias on the scaled scores,
                               softmax(scale*QK^T + key_bias[bias_sel[b]]) — the fore-/background key masks of
                               MutualSelfAttentionControlMask / MaskAuto (masactrl/model/attention_control.py:139-147,
-                              238-246; "masked" keys carry finfo.min, as there). mma kernel only; no second K/V block. */
+                              238-246; "masked" keys carry finfo.min, as there). Served by the mma kernel and, for head_dim <= 64, by a
+                              variant of the tcgen05 kernel; no second K/V block. */
   const int32_t* bias_sel; /* HOST [B] or NULL (= no bias): row b uses key_bias[bias_sel[b]]; <0 = no bias for that row */
   int32_t n_bias;
   void* workspace;         /* optional device scratch of >= ief_attn_workspace_bytes(p) bytes (16-byte aligned), or NULL. With it the

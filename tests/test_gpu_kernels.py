@@ -207,18 +207,26 @@ def test_attn_key_bias_masked_masactrl(cuda, shape):
     full = torch.stack([bias[s_] if s_ >= 0 else torch.zeros(M) for s_ in sel])
     p = orc.attention_probs(q, k[src], H, scale, key_bias=full)
     want = orc.apply_probs(p, v[src], H)
-    got = ops.attention(q.to(cuda), k.to(cuda), v.to(cuda), H, scale, k_src=src, v_src=src, key_bias=bias.to(cuda), bias_sel=sel)
-    torch.cuda.synchronize()
-    assert _cabi.last_attn_impl() == "mma"
-    err = (got.float().cpu() - want).abs().max().item()
-    assert err < TOL, f"max abs err {err}"
-    if 2 in sel:  # all keys masked -> uniform average of V
-        b = sel.index(2)
-        assert (got[b].float().cpu() - v[src[b]].float().mean(0, keepdim=True)).abs().max().item() < TOL
-    with pytest.raises(_cabi.IefError):
-        ops.attention(q.to(cuda), k.to(cuda), v.to(cuda), H, scale, key_bias=bias.to(cuda), bias_sel=sel, impl=ops.IEF_IMPL_TCGEN05)
+    impls = [ops.IEF_IMPL_MMA, ops.IEF_IMPL_AUTO] + ([ops.IEF_IMPL_TCGEN05] if d <= 64 else [])
+    for impl in impls:
+        got = ops.attention(q.to(cuda), k.to(cuda), v.to(cuda), H, scale, k_src=src, v_src=src, key_bias=bias.to(cuda), bias_sel=sel, impl=impl)
+        torch.cuda.synchronize()
+        if impl == ops.IEF_IMPL_TCGEN05 or (impl == ops.IEF_IMPL_AUTO and d <= 64 and N >= 512):
+            assert _cabi.last_attn_impl() == "tcgen05"   # head_dim <= 64: the biased variant of the third-generation kernel
+        elif impl == ops.IEF_IMPL_MMA or d > 64:
+            assert _cabi.last_attn_impl() == "mma"
+        err = (got.float().cpu() - want).abs().max().item()
+        assert err < TOL, f"impl {impl}: max abs err {err}"
+        if 2 in sel:  # all keys masked -> uniform average of V
+            b = sel.index(2)
+            assert (got[b].float().cpu() - v[src[b]].float().mean(0, keepdim=True)).abs().max().item() < TOL
+    if d > 64:
+        with pytest.raises(_cabi.IefError):
+            ops.attention(q.to(cuda), k.to(cuda), v.to(cuda), H, scale, key_bias=bias.to(cuda), bias_sel=sel, impl=ops.IEF_IMPL_TCGEN05)
     with pytest.raises(_cabi.IefError):
         ops.attention(q.to(cuda), k.to(cuda), v.to(cuda), H, scale, key_bias=bias.to(cuda), bias_sel=[0, 1, 2, 7])
+    with pytest.raises(_cabi.IefError):
+        ops.attention(q.to(cuda), k.to(cuda), v.to(cuda), H, scale, key_bias=bias.to(cuda), bias_sel=sel, k_src2=src, v_src2=src)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
