@@ -262,12 +262,13 @@ def test_attn_rejects_bad_arguments(cuda):
 def _edit_tables(n_tgt, M, seed, mode):
     g = torch.Generator().manual_seed(seed)
     alpha = (torch.rand(n_tgt, M, generator=g) > 0.3).float()
-    if mode == "replace":
+    if mode in ("replace", "replace_dense"):
         mapper = torch.eye(M).repeat(n_tgt, 1, 1)
         mapper[:, 3, 3] = 0
         mapper[:, 3, 4] = 0.5
         mapper[:, 3, 5] = 0.5
-        mapper[:, 10:14] = torch.rand(n_tgt, 4, M, generator=g).softmax(-1)
+        rows = 4 if mode == "replace" else 20   # 20 dense rows: > 8 source tokens per target token -> the dense-mapper flavour
+        mapper[:, 10:10 + rows] = torch.rand(n_tgt, rows, M, generator=g).softmax(-1)
         return dict(mapper=mapper), alpha
     if mode == "refine":
         idx = torch.arange(M).repeat(n_tgt, 1)
@@ -281,7 +282,7 @@ def _edit_tables(n_tgt, M, seed, mode):
     return {}, alpha
 
 
-@pytest.mark.parametrize("mode", ["replace", "refine", "none"])
+@pytest.mark.parametrize("mode", ["replace", "replace_dense", "refine", "none"])
 @pytest.mark.parametrize("equalize", [False, True])
 @pytest.mark.parametrize("shape", [(4, 8, 1024, 77, 80), (6, 2, 300, 77, 40), (4, 8, 4096, 77, 40)])
 def test_cross_attention_edit(cuda, mode, equalize, shape):
@@ -298,17 +299,19 @@ def test_cross_attention_edit(cuda, mode, equalize, shape):
         eq[:, 6] = -1.5
     alpha_table = alpha.reshape(1, n_tgt, 1, 1, M)
     probs = orc.attention_probs(q, k, H, scale)
-    edited = orc.p2p_edit_probs(probs, H, n_prompts, True, 0, mode=mode, alpha_table=alpha_table, equalizer=eq, **tables)
+    edited = orc.p2p_edit_probs(probs, H, n_prompts, True, 0, mode=mode.split("_")[0], alpha_table=alpha_table, equalizer=eq, **tables)
     want_o = orc.apply_probs(edited, v, H)
     dev = {}
-    if mode == "replace":
+    if mode.startswith("replace"):
         dev["mapper"] = tables["mapper"].to(cuda).contiguous()
     if mode == "refine":
         dev["mapper_idx"] = tables["mapper"].to(torch.int32).to(cuda).contiguous()
         dev["refine_alpha"] = tables["refine_alphas"].reshape(n_tgt, M).to(cuda).contiguous()
     if eq is not None:
         dev["equalizer"] = eq.to(cuda).contiguous()
-    edit = ops.CrossEdit({"replace": ops.IEF_EDIT_REPLACE, "refine": ops.IEF_EDIT_REFINE, "none": ops.IEF_EDIT_NONE}[mode], n_tgt, **dev)
+    edit = ops.CrossEdit({"replace": ops.IEF_EDIT_REPLACE, "refine": ops.IEF_EDIT_REFINE, "none": ops.IEF_EDIT_NONE}[mode.split("_")[0]], n_tgt, **dev)
+    if mode.startswith("replace"):
+        assert (edit.mapper_nz_idx is None) == (mode == "replace_dense")   # sparse form unless a column has more than 8 non-zeros
     lo = B // 2
     base = [-1] * B
     slot = [0] * B

@@ -402,3 +402,24 @@ def test_pix2pix_zero_loops_reproduce_reference(monkeypatch):
     # the guidance matters: without it the edit loop lands elsewhere
     moved = (g["edit_no_guidance"] - g["edit_per_step"][-1]).abs().max()
     assert moved > 20 * (edit - g["edit_per_step"][-1]).abs().max(), moved
+
+
+def test_cross_edit_sparse_mapper_form():
+    """ops.CrossEdit.sparsify: per target token the (<= 8) contributing source tokens in ascending order, -1 padded; a mapper
+    with a denser column yields (None, None) and the kernel multiplies the dense form."""
+    from image_editing_framework_b200 import ops
+    m = torch.eye(77).repeat(2, 1, 1)
+    m[0, 3, 3], m[0, 3, 4], m[0, 3, 5] = 0.0, 0.5, 0.5
+    m[1, 10:14] = torch.rand(4, 77, generator=torch.Generator().manual_seed(0)).softmax(-1)
+    idx, w = ops.CrossEdit.sparsify(m)
+    assert idx.shape == (2, 77, 8) and idx.dtype == torch.int32 and w.dtype == torch.float32
+    dense = torch.zeros_like(m)
+    for s_ in range(2):
+        for n in range(77):
+            nz = idx[s_, n][idx[s_, n] >= 0]
+            assert torch.equal(nz, nz.sort().values)
+            dense[s_, nz.long(), n] = w[s_, n, :len(nz)]
+    assert torch.equal(dense, m)
+    assert idx[0, 3].tolist() == [-1] * 8 and idx[0, 4].tolist()[:2] == [3, 4]
+    m[1, 10:30] = 1.0 / 77
+    assert ops.CrossEdit.sparsify(m) == (None, None)
