@@ -11,7 +11,7 @@ import os
 import subprocess
 import threading
 
-IEF_ABI_VERSION = 4
+IEF_ABI_VERSION = 5
 IEF_MAX_ROWS = 64
 
 IEF_BF16, IEF_F16, IEF_F32 = 0, 1, 2
@@ -65,6 +65,17 @@ class CrossParams(C.Structure):
     ]
 
 
+class CrossBwdParams(C.Structure):
+    _fields_ = [
+        ("q", Tensor4), ("k", Tensor4), ("v", Tensor4), ("dout", Tensor4), ("dq", Tensor4),
+        ("dtype", C.c_int32),
+        ("B", C.c_int32), ("H", C.c_int32), ("Nq", C.c_int32), ("Nk", C.c_int32), ("d", C.c_int32),
+        ("scale", C.c_float),
+        ("dprobs", C.c_void_p),
+        ("ds_out", C.c_void_p),
+    ]
+
+
 class LocalBlendParams(C.Structure):
     _fields_ = [
         ("maps", C.POINTER(C.c_void_p)), ("map_heads", C.POINTER(C.c_int32)),
@@ -88,7 +99,7 @@ class UmmaProbeParams(C.Structure):
 
 # every symbol include/ief_b200.h declares; tests check the .so exports each one
 EXPORTS = (
-    "ief_attn_fwd", "ief_attn_workspace_bytes", "ief_cross_attn_edit_fwd", "ief_store_accumulate", "ief_local_blend", "ief_mask_blend", "ief_cfg_ddim_step",
+    "ief_attn_fwd", "ief_attn_workspace_bytes", "ief_cross_attn_edit_fwd", "ief_cross_attn_bwd", "ief_store_accumulate", "ief_local_blend", "ief_mask_blend", "ief_cfg_ddim_step",
     "ief_umma_probe", "ief_abi_version", "ief_last_error", "ief_launch_count", "ief_last_attn_impl", "ief_check_device",
 )
 
@@ -148,6 +159,8 @@ def lib() -> C.CDLL:
         L.ief_attn_workspace_bytes.restype = C.c_int64
         L.ief_cross_attn_edit_fwd.argtypes = [C.POINTER(CrossParams), C.c_void_p]
         L.ief_cross_attn_edit_fwd.restype = C.c_int
+        L.ief_cross_attn_bwd.argtypes = [C.POINTER(CrossBwdParams), C.c_void_p]
+        L.ief_cross_attn_bwd.restype = C.c_int
         L.ief_store_accumulate.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int32, C.c_void_p]
         L.ief_store_accumulate.restype = C.c_int
         L.ief_local_blend.argtypes = [C.POINTER(LocalBlendParams), C.c_void_p]

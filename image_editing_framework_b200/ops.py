@@ -203,6 +203,34 @@ def cross_attention_edit(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, head
     return out
 
 
+def cross_attention_backward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, dout: torch.Tensor, heads: int, scale: float, *,
+                             dprobs: Optional[torch.Tensor] = None, want_ds: bool = True):
+    """Backward of plain <= 80-key cross-attention (ief_cross_attn_bwd): returns (dQ [B, N, H*d] in q's dtype, dS fp32
+    [B*heads, N, Nk] or None). dprobs: gradient arriving directly on the probabilities, fp32 [B*heads, N, Nk]."""
+    _require_cuda(q, k, v, dout, dprobs)
+    if q.dtype not in (torch.bfloat16, torch.float16) or k.dtype != q.dtype or v.dtype != q.dtype or dout.dtype != q.dtype:
+        raise TypeError(f"cross_attention_backward needs matching bf16/fp16 q,k,v,dout; got {q.dtype}, {k.dtype}, {v.dtype}, {dout.dtype}")
+    q4, k4, v4, g4 = _as4(q, heads), _as4(k, heads), _as4(v, heads), _as4(dout, heads)
+    B, Nq, _, d = q4.shape
+    Nk = k4.shape[1]
+    dq = torch.empty((B, Nq, heads * d), dtype=q.dtype, device=q.device)
+    p = _cabi.CrossBwdParams()
+    p.q, p.k, p.v, p.dout, p.dq = _t4(q4, heads), _t4(k4, heads), _t4(v4, heads), _t4(g4, heads), _t4(dq, heads)
+    p.dtype = _DTYPES[q.dtype]
+    p.B, p.H, p.Nq, p.Nk, p.d = B, heads, Nq, Nk, d
+    p.scale = float(scale)
+    if dprobs is not None:
+        if dprobs.dtype != torch.float32 or not dprobs.is_contiguous() or dprobs.numel() != B * heads * Nq * Nk:
+            raise TypeError("dprobs must be a contiguous fp32 [B*heads, Nq, Nk] tensor")
+        p.dprobs = dprobs.data_ptr()
+    ds = torch.empty((B * heads, Nq, Nk), dtype=torch.float32, device=q.device) if want_ds else None
+    if ds is not None:
+        p.ds_out = ds.data_ptr()
+    with torch.cuda.device(q.device):
+        _cabi.check("ief_cross_attn_bwd", _cabi.lib().ief_cross_attn_bwd(C.byref(p), _stream()))
+    return dq, ds
+
+
 def store_accumulate(dst: Sequence[torch.Tensor], src: Sequence[torch.Tensor]) -> None:
     """dst[i] += src[i] for all i in one launch (ief_store_accumulate)."""
     if len(dst) != len(src):

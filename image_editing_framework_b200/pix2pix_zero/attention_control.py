@@ -5,15 +5,54 @@ Under `torch.no_grad()` (two of the three UNet passes per step, pix2pix-zero/mod
 the processor runs the fused kernels: cross-attention layers emit their [B*heads, N, 77] fp32 probabilities straight
 from the kernel into `attn.attn_probs` (:46 — the only maps the method ever reads, sd_utils.py:108-110,169-171);
 self-attention layers run the flash kernel and stash nothing (the reference keeps every 4096^2 map alive, unread).
-When autograd is recording (the guidance pass, sd_utils.py:163-174) the probabilities must stay differentiable, which a
-forward-only kernel cannot serve: that pass runs the reference's torch arithmetic, as SURVEY.md section 8 scopes it.
+When autograd is recording (the guidance pass, sd_utils.py:163-174) the cross-attention probabilities must stay
+differentiable: on CUDA they come from `_CrossAttention`, an autograd Function over the forward kernel and
+ief_cross_attn_bwd; self-attention layers (maps never read) use library SDPA; on CPU, with an attention mask or with
+IEF_P2Z_KERNEL_BACKWARD=0 the pass runs the reference's torch arithmetic.
 """
 from __future__ import annotations
 
 import torch
 
 from .. import ops
-from ..hooks import project_qkv, reject_mask
+import os
+
+from ..hooks import compute_dtype, project_qkv, reject_mask
+
+
+def _kernel_backward_enabled() -> bool:
+    return os.environ.get("IEF_P2Z_KERNEL_BACKWARD", "1") != "0"
+
+
+class _CrossAttention(torch.autograd.Function):
+    """Differentiable 77-key cross-attention on the kernels: forward = ief_cross_attn_edit_fwd with the probability output (the
+    maps the guidance loss is built on), backward = ief_cross_attn_bwd (dQ, dS) plus two small batched GEMMs for dK and dV."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, heads: int, scale: float):
+        B, N, M = q.shape[0], q.shape[1], k.shape[1]
+        probs = torch.empty((B * heads, N, M), dtype=torch.float32, device=q.device)
+        out = ops.cross_attention_edit(q, k, v, heads, scale, probs_out=probs)
+        ctx.save_for_backward(q, k, v, probs)
+        ctx.heads, ctx.scale = heads, scale
+        return out, probs
+
+    @staticmethod
+    def backward(ctx, dout, dprobs):
+        q, k, v, probs = ctx.saved_tensors
+        heads, scale = ctx.heads, ctx.scale
+        need_kv = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        dprobs = None if dprobs is None else dprobs.contiguous().float()
+        dq, ds = ops.cross_attention_backward(q, k, v, dout.contiguous().to(q.dtype), heads, scale, dprobs=dprobs, want_ds=need_kv)
+        dk = dv = None
+        if need_kv:
+            B, N, C = q.shape
+            M, d = k.shape[1], C // heads
+            qh = q.reshape(B, N, heads, d).permute(0, 2, 1, 3).reshape(B * heads, N, d).float()
+            gh = dout.reshape(B, N, heads, d).permute(0, 2, 1, 3).reshape(B * heads, N, d).float()
+            dk = torch.bmm(ds.transpose(1, 2), qh).reshape(B, heads, M, d).permute(0, 2, 1, 3).reshape(B, M, C).to(k.dtype)   # dK = dS^T Q
+            dv = torch.bmm(probs.transpose(1, 2), gh).reshape(B, heads, M, d).permute(0, 2, 1, 3).reshape(B, M, C).to(v.dtype)  # dV = P^T dO
+        return dq, dk, dv, None, None
 
 
 class MyAttnProcessor:
@@ -74,6 +113,13 @@ class MyAttnProcessor:
             out = torch.nn.functional.scaled_dot_product_attention(q4, k4, v4, scale=attn.scale)
             attn.attn_probs = None
             return out.transpose(1, 2).reshape(q.shape[0], q.shape[1], -1)
+        if context is not None and hidden_states.is_cuda and attention_mask is None and context.shape[1] <= 80 and _kernel_backward_enabled():
+            # the maps the loss reads, with their gradient, on the fused kernels (forward + ief_cross_attn_bwd)
+            q, k, v = attn.to_q(hidden_states), attn.to_k(src), attn.to_v(src)
+            dt = compute_dtype(q)
+            out, probs = _CrossAttention.apply(q.to(dt), k.to(dt), v.to(dt), attn.heads, attn.scale)
+            attn.attn_probs = probs
+            return out.to(q.dtype)
         q = attn.head_to_batch_dim(attn.to_q(hidden_states))
         k = attn.head_to_batch_dim(attn.to_k(src))
         v = attn.head_to_batch_dim(attn.to_v(src))

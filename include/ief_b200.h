@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define IEF_ABI_VERSION 4
+#define IEF_ABI_VERSION 5
 #define IEF_MAX_ROWS 64  /* max UNet batch rows per call (reference uses 1, 2 or 4) */
 #define IEF_MAX_WORDS 77 /* CLIP context length, p2p/model/ptp_utils.py:8 MAX_NUM_WORDS */
 
@@ -150,6 +150,26 @@ typedef struct ief_cross_params {
 } ief_cross_params;
 
 int ief_cross_attn_edit_fwd(const ief_cross_params* p, void* stream);
+
+/*
+ * ief_cross_attn_bwd — backward of the (un-edited) <= 80-key cross-attention, for Pix2Pix-zero's guidance pass
+ * (pix2pix-zero/model/sd_utils.py:163-174: loss = sum over attn2 layers of ||attn_probs - ref||^2, differentiated
+ * with respect to the latents; forward: pix2pix-zero/model/attention_control.py:43-49).
+ *     P = softmax(scale Q K^T) is recomputed;  dP = dO V^T + dprobs;  dS = P * (dP - rowsum(P * dP)) * scale;  dQ = dS K
+ * q, k, v, dout, dq: strided [B, N, H, d] views (bf16 / fp16); dprobs: fp32 [B*H, Nq, Nk], the gradient arriving directly on
+ * the probabilities (NULL = none); ds_out: fp32 [B*H, Nq, Nk] or NULL — when given, dS is stored so that the caller can
+ * form dK = dS^T Q and dV = P^T dO (two 77 x d reductions over the query axis) with batched GEMMs.
+ */
+typedef struct ief_cross_bwd_params {
+  ief_tensor4 q, k, v, dout, dq;
+  int32_t dtype;
+  int32_t B, H, Nq, Nk, d;
+  float scale;
+  const float* dprobs;
+  float* ds_out;
+} ief_cross_bwd_params;
+
+int ief_cross_attn_bwd(const ief_cross_bwd_params* p, void* stream);
 
 /*
  * ief_store_accumulate — dst[i][:] += src[i][:] for n tensors in ONE launch

@@ -460,3 +460,41 @@ def test_attn_workspace_contract(cuda):
     for r in results:
         assert (r - want).abs().max().item() < TOL
     assert torch.equal(results[0], results[1])          # too small a workspace is ignored: identical launches
+
+
+@pytest.mark.parametrize("shape", [(2, 8, 1024, 77, 40), (2, 4, 300, 77, 80), (1, 2, 256, 77, 160), (2, 2, 4096, 64, 64)])
+@pytest.mark.parametrize("with_dprobs", [True, False])
+def test_cross_attention_backward(cuda, shape, with_dprobs):
+    """ief_cross_attn_bwd through the autograd Function of the Pix2Pix-zero processor: dQ, dK, dV of
+    loss = <O, W_o> + <P, W_p> against torch autograd on the fp32 materialised formulation."""
+    from image_editing_framework_b200.pix2pix_zero.attention_control import _CrossAttention
+    B, H, N, M, d = shape
+    q, k, v = _qkv(B, N, M, H, d, 17)
+    scale = d ** -0.5
+    g = torch.Generator().manual_seed(18)
+    wo = torch.randn(B, N, H * d, generator=g)
+    wp = torch.randn(B * H, N, M, generator=g) if with_dprobs else None
+    # reference: fp32 autograd on the bf16-rounded inputs
+    qf, kf, vf = (t.float().clone().requires_grad_(True) for t in (q, k, v))
+    p_ref = orc.attention_probs(qf, kf, H, scale)
+    o_ref = orc.apply_probs(p_ref, vf, H)
+    loss = (o_ref * wo).sum() + ((p_ref * wp).sum() if with_dprobs else 0.0)
+    loss.backward()
+    # kernels
+    qc, kc, vc = (t.to(cuda).clone().requires_grad_(True) for t in (q, k, v))
+    out, probs = _CrossAttention.apply(qc, kc, vc, H, scale)
+    loss_c = (out.float() * wo.to(cuda)).sum() + ((probs * wp.to(cuda)).sum() if with_dprobs else 0.0)
+    loss_c.backward()
+    torch.cuda.synchronize()
+    assert (probs.cpu() - p_ref.detach()).abs().max().item() < 5e-3
+    for name, got, want in (("dq", qc.grad, qf.grad), ("dk", kc.grad, kf.grad), ("dv", vc.grad, vf.grad)):
+        err = (got.float().cpu() - want).abs().max().item()
+        ref = want.abs().max().item()
+        assert err <= 2e-2 * ref + 1e-3, f"{name}: max abs err {err} vs max |grad| {ref}"
+    # dQ alone (K, V detached): no dS output requested
+    qd = q.to(cuda).clone().requires_grad_(True)
+    out2, _ = _CrossAttention.apply(qd, k.to(cuda), v.to(cuda), H, scale)
+    (out2.float() * wo.to(cuda)).sum().backward()
+    qf2 = q.float().clone().requires_grad_(True)
+    (orc.apply_probs(orc.attention_probs(qf2, k.float(), H, scale), v.float(), H) * wo).sum().backward()
+    assert (qd.grad.float().cpu() - qf2.grad).abs().max().item() <= 2e-2 * qf2.grad.abs().max().item() + 1e-3
