@@ -130,6 +130,10 @@ class AttentionStore(AttentionControl):
         self.attention_store: Dict[str, List[torch.Tensor]] = {}
         self._slot = self._zero_slots()
         self._store_enabled = True
+        # Opt-in (not reference behaviour): keep only the maps a LocalBlend reads (cross-attention at its resolution). The other
+        # store entries become None placeholders so list positions stay the reference's; get_average_attention skips them.
+        self.lean_store = False
+        self._lean_tokens: Optional[int] = None
         self._spare: Dict[str, List[torch.Tensor]] = {}  # buffers of the store before the last reset(), reused in place
 
     @staticmethod
@@ -150,7 +154,7 @@ class AttentionStore(AttentionControl):
         if i == len(bufs):
             spare = self._spare.get(key, [])
             shape = (rows * heads, n, m)
-            if i < len(spare) and tuple(spare[i].shape) == shape and spare[i].device == torch.device(device):
+            if i < len(spare) and spare[i] is not None and tuple(spare[i].shape) == shape and spare[i].device == torch.device(device):
                 bufs.append(spare[i])  # same storage as before reset(): captured graphs keep pointing at live memory
             else:
                 bufs.append(torch.empty(shape, dtype=torch.float32, device=device))
@@ -159,6 +163,19 @@ class AttentionStore(AttentionControl):
 
     def _stores(self, n_tokens: int) -> bool:
         return self._store_enabled and n_tokens <= _STORE_MAX_TOKENS
+
+    def _wanted(self, n_tokens: int, is_cross: bool) -> bool:
+        return not self.lean_store or self._lean_tokens is None or (is_cross and n_tokens == self._lean_tokens)
+
+    def _skip_slot(self, key: str) -> None:
+        """Lean store: this layer's maps are not kept; a None placeholder preserves the list positions LocalBlend slices by."""
+        if len(self.attention_store) == 0:
+            self.attention_store = self.get_empty_store()
+        bufs = self.attention_store[key]
+        i = self._slot[key]
+        self._slot[key] = i + 1
+        if i == len(bufs):
+            bufs.append(None)
 
     def fused_forward(self, q, k, v, heads, scale, is_cross, place_in_unet):
         return self._attend_and_store(q, k, v, heads, scale, is_cross, place_in_unet)
@@ -169,8 +186,11 @@ class AttentionStore(AttentionControl):
         probs = accum = slots = None
         if self._stores(N):
             key = f"{place_in_unet}_{'cross' if is_cross else 'self'}"
-            probs, accum = self._store_target(key, hi - lo, heads, N, M, q.device)
-            slots = [(b - lo) if lo <= b < hi else -1 for b in range(B)]
+            if self._wanted(N, is_cross):
+                probs, accum = self._store_target(key, hi - lo, heads, N, M, q.device)
+                slots = [(b - lo) if lo <= b < hi else -1 for b in range(B)]
+            else:
+                self._skip_slot(key)
         if is_cross:
             if M > 80:
                 raise NotImplementedError(f"cross-attention with {M} keys: the fused edit kernel holds at most 80")
@@ -182,7 +202,7 @@ class AttentionStore(AttentionControl):
         self._slot = self._zero_slots()
 
     def get_average_attention(self):
-        return {key: [item / self.cur_step for item in self.attention_store[key]] for key in self.attention_store}
+        return {key: [None if item is None else item / self.cur_step for item in self.attention_store[key]] for key in self.attention_store}
 
     def graph_key(self):
         base = super().graph_key()
@@ -224,6 +244,7 @@ class AttentionControlEdit(AttentionStore, abc.ABC):
         self.num_self_replace = int(num_steps * self_replace_steps[0]), int(num_steps * self_replace_steps[1])
         self.local_blend = local_blend
         self._store_enabled = local_blend is not None
+        self._lean_tokens = local_blend.res ** 2 if local_blend is not None else None
         self._device = torch.device(device)
         # [num_steps+1, n_targets, 77] fp32 contiguous: row `cur_step` is handed to the kernel as-is
         self._alpha_table = self.cross_replace_alpha.reshape(num_steps + 1, self.batch_size - 1, -1).to(torch.float32).contiguous()

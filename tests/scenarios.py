@@ -178,12 +178,13 @@ def run_pix2pix_zero_loop(g, device, guidance_amount=None, graphs=False):
     return rec.float().cpu(), edit.float().cpu()
 
 
-def run_p2p_localblend(g, device):
+def run_p2p_localblend(g, device, lean_store=False):
     cfg = UNetConfig(**g["config"])
     pipe = make_pipeline(cfg, seed=g["pipe_seed"], device=device)
     prompts, steps = g["prompts"], g["steps"]
     lb = p2p.LocalBlend(pipe.tokenizer, prompts, g["blend_words"], device=device)
     ctrl = p2p.AttentionReplace(prompts, pipe.tokenizer, steps, 0.8, 0.6, lb, device=device)
+    ctrl.lean_store = lean_store
     pipe.scheduler.set_timesteps(steps)
     p2p.register_attention_control(pipe, ctrl)
     context = editing.encode_prompts(pipe, prompts)

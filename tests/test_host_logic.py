@@ -423,3 +423,18 @@ def test_cross_edit_sparse_mapper_form():
     assert idx[0, 3].tolist() == [-1] * 8 and idx[0, 4].tolist()[:2] == [3, 4]
     m[1, 10:30] = 1.0 / 77
     assert ops.CrossEdit.sparsify(m) == (None, None)
+
+
+def test_lean_store_keeps_localblend_result(monkeypatch):
+    """controller.lean_store = True (opt-in): only the 16x16 cross maps LocalBlend reads are stored, the other entries are None
+    placeholders at the reference's list positions; the edit result is unchanged."""
+    cpu_backend.install(monkeypatch)
+    g = golden("p2p_localblend.pt")
+    full = scenarios.run_p2p_localblend(g, torch.device("cpu"))
+    lean = scenarios.run_p2p_localblend(g, torch.device("cpu"), lean_store=True)
+    assert torch.equal(full[1][-1], lean[1][-1])
+    store = lean[0].attention_store
+    assert all(m is None for m in store["down_self"] + store["up_self"] + store["mid_self"])
+    kept = [m for key in ("down_cross", "up_cross", "mid_cross") for m in store[key] if m is not None]
+    assert len(kept) == 5 and all(m.shape[1] == 256 for m in kept)
+    assert [m is None for m in store["down_cross"]] == [True, True, False, False]

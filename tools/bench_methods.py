@@ -92,6 +92,10 @@ def main():
             for p_ in unet.parameters():
                 p_.requires_grad = False
 
+    def _lean(ctrl):
+        ctrl.lean_store = True
+        return ctrl
+
     eq = p2p.seq_aligner.get_equalizer(tok, PROMPTS[1], ("dog",), (3.0,))
     cases = [
         ("p2p EmptyControl (plain sampling)", p2p_run(lambda: p2p.EmptyControl(False))),
@@ -101,6 +105,8 @@ def main():
         ("p2p AttentionStore", p2p_run(lambda: p2p.AttentionStore(False))),
         ("p2p AttentionReplace + LocalBlend (store on)", p2p_run(lambda: p2p.AttentionReplace(
             local_blend=p2p.LocalBlend(tok, PROMPTS, [["cat"], ["dog"]], device=dev), **common))),
+        ("p2p AttentionReplace + LocalBlend, lean_store (opt-in)", p2p_run(lambda: _lean(p2p.AttentionReplace(
+            local_blend=p2p.LocalBlend(tok, PROMPTS, [["cat"], ["dog"]], device=dev), **common)))),
         ("masactrl MutualSelfAttentionControl(4, 10)", masa_run(lambda: masactrl.MutualSelfAttentionControl(4, 10, total_steps=STEPS))),
         ("masactrl Union", masa_run(lambda: masactrl.MutualSelfAttentionControlUnion(4, 10, total_steps=STEPS))),
         ("masactrl MaskAuto", masa_run(lambda: masactrl.MutualSelfAttentionControlMaskAuto(4, 10, total_steps=STEPS, ref_token_idx=[5], cur_token_idx=[5]))),
