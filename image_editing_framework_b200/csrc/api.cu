@@ -73,6 +73,20 @@ extern "C" int ief_attn_fwd(const ief_attn_params* p, void* stream) {
   int impl = p->impl;
   if (p->probs_out) {
     IEF_REQUIRE(impl != IEF_IMPL_TCGEN05, IEF_ERR_UNSUPPORTED, "ief_attn_fwd: probs_out is only produced by the mma kernel");
+    if (impl == IEF_IMPL_AUTO && ief_attn_probs_via_lse(p) && p->workspace != nullptr &&
+        p->workspace_bytes >= (int64_t)p->B * p->H * p->Nq * (int64_t)sizeof(float)) {
+      // O and the row log-sum-exp from the tcgen05 kernel, then one QK^T sweep writes / accumulates the maps
+      IEF_REQUIRE((reinterpret_cast<uintptr_t>(p->workspace) & 15) == 0, IEF_ERR_INVALID, "ief_attn_fwd: workspace must be 16-byte aligned");
+      ief_attn_params o_only = *p;
+      o_only.probs_out = nullptr;
+      o_only.workspace = nullptr;
+      o_only.workspace_bytes = 0;
+      float* lse = static_cast<float*>(p->workspace);
+      g_last_impl = "tcgen05+probs";
+      const int rc = ief_attn_tc_launch(&o_only, rows, st, lse);
+      if (rc != IEF_OK) return rc;
+      return ief_attn_probs_from_lse_launch(p, rows, lse, st);
+    }
     impl = IEF_IMPL_MMA;
   }
   if (any_bias) {

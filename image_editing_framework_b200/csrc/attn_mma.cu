@@ -247,6 +247,132 @@ int launch_dp(const MmaArgs& a, dim3 grid, cudaStream_t st) {
   return launch_one<DTYPE, 160, WRITE_P>(a, grid, st);
 }
 
+// Probabilities only, from a known row log-sum-exp (log2 units): P = exp2(scale_log2 * Q K^T - lse). One sweep over the keys, no V,
+// no running statistics: used behind the tcgen05 kernels, which produce O and the lse, so that stored maps cost one QK^T on
+// mma.sync plus the HBM traffic of the maps instead of the two-sweep kernel above.
+template <int DTYPE, int DP>
+__global__ void __launch_bounds__(kThreads)
+attn_probs_from_lse_kernel(const __grid_constant__ MmaArgs a, const float* __restrict__ lse, int nqt, int ksplit) {
+  using E = ElemT<DTYPE>;
+  using T = typename E::T;
+  constexpr int LD = DP + 8, KS = DP / 16;
+  // grid.x = query tiles x key splits: there is no reduction over the keys, so the key range is spread over several CTAs to
+  // keep enough of them in flight (the sweep is bound by the latency of the map read-modify-write, not by arithmetic)
+  const int b = blockIdx.z, h = blockIdx.y, qt = blockIdx.x % nqt, split = blockIdx.x / nqt;
+  if (!a.rows.active[b] || a.rows.pslot[b] < 0) return;
+  extern __shared__ uint4 smem4[];
+  T* sQ = reinterpret_cast<T*>(smem4);
+  T* sKs = sQ + kBM * LD;  // two stages of K
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int nk_total = a.Nk * (a.nt2 > 0 ? 2 : 1);
+  const int nt_all = a.nt1 + a.nt2;
+  const int j_begin = (int)((long)nt_all * split / ksplit), j_end = (int)((long)nt_all * (split + 1) / ksplit);
+  auto fetch = [&](int j) {
+    const bool blk2 = j >= a.nt1;
+    const int jj = blk2 ? j - a.nt1 : j;
+    const int kb = blk2 ? a.rows.k2[b] : a.rows.k[b];
+    const T* kg = reinterpret_cast<const T*>(a.k.ptr) + (int64_t)kb * a.k.stride_b + (int64_t)h * a.k.stride_h;
+    load_tile_async<T, kBN, DP, LD, kThreads>(sKs + (j & 1) * kBN * LD, kg, a.k.stride_n, jj * kBN, a.Nk, a.d, tid);
+    cp_async_commit();
+  };
+  const T* qg = reinterpret_cast<const T*>(a.q.ptr) + (int64_t)a.rows.q[b] * a.q.stride_b + (int64_t)h * a.q.stride_h;
+  load_tile_async<T, kBM, DP, LD, kThreads>(sQ, qg, a.q.stride_n, qt * kBM, a.Nq, a.d, tid);
+  if (j_begin >= j_end) return;
+  fetch(j_begin);
+  const int grow0 = qt * kBM + warp * 16 + g;
+  const int64_t lrow = ((int64_t)b * a.H + h) * a.Nq;
+  const float lse0 = grow0 < a.Nq ? __ldg(lse + lrow + grow0) : 0.f, lse1 = grow0 + 8 < a.Nq ? __ldg(lse + lrow + grow0 + 8) : 0.f;
+  const float c2 = a.scale_log2;
+  const int64_t prow = ((int64_t)a.rows.pslot[b] * a.H + h) * a.Nq;
+  uint32_t qf[KS][4];
+#pragma unroll 1
+  for (int j = j_begin; j < j_end; ++j) {
+    const bool blk2 = j >= a.nt1;
+    const int jj = blk2 ? j - a.nt1 : j;
+    const T* sK = sKs + (j & 1) * kBN * LD;
+    cp_async_wait<0>();
+    __syncthreads();
+    if (j + 1 < j_end) fetch(j + 1);
+    if (j == j_begin) {
+#pragma unroll
+      for (int kk = 0; kk < KS; ++kk) ldsm_x4(qf[kk], &sQ[(warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LD + kk * 16 + (lane >> 4) * 8]);
+    }
+    float s[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < KS; ++kk) {
+#pragma unroll
+      for (int nb2 = 0; nb2 < 4; ++nb2) {
+        uint32_t bf[4];
+        ldsm_x4(bf, &sK[(nb2 * 16 + (lane & 7) + (lane >> 4) * 8) * LD + kk * 16 + ((lane >> 3) & 1) * 8]);
+        mma16816<DTYPE>(s[2 * nb2], qf[kk], bf[0], bf[1]);
+        mma16816<DTYPE>(s[2 * nb2 + 1], qf[kk], bf[2], bf[3]);
+      }
+    }
+    const int vc = min(kBN, a.Nk - jj * kBN);
+    const int col0 = (blk2 ? a.Nk : 0) + jj * kBN;
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+      const int c = nb * 8 + 2 * t;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int r = grow0 + hh * 8;
+        if (r < a.Nq) {
+          const float ls = hh ? lse1 : lse0;
+          float* dst = a.probs + (prow + r) * nk_total + col0 + c;
+          const float p0 = ief_exp2(fmaf(s[nb][2 * hh], c2, -ls)), p1 = ief_exp2(fmaf(s[nb][2 * hh + 1], c2, -ls));
+          if (c + 1 < vc) {  // the pair as one 8-byte access (rows are 8-byte aligned when the key count is even)
+            if ((nk_total & 1) == 0) {
+              float2* d2 = reinterpret_cast<float2*>(dst);
+              float2 old = a.probs_accum ? *d2 : make_float2(0.f, 0.f);
+              *d2 = make_float2(old.x + p0, old.y + p1);
+            } else {
+              dst[0] = a.probs_accum ? dst[0] + p0 : p0;
+              dst[1] = a.probs_accum ? dst[1] + p1 : p1;
+            }
+          } else if (c < vc) {
+            dst[0] = a.probs_accum ? dst[0] + p0 : p0;
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int DTYPE, int DP>
+int launch_probs_one(const MmaArgs& a, const float* lse, dim3 grid, cudaStream_t st) {
+  constexpr int smem = (kBM + 2 * kBN) * (DP + 8) * 2;
+  auto kern = attn_probs_from_lse_kernel<DTYPE, DP>;
+  static bool configured = false;
+  if (!configured) {
+    IEF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  // enough CTAs for ~6 per SM: split the key range when the (row, head, query tile) grid alone is too small
+  int stored_rows = 0;
+  for (int i = 0; i < a.B; ++i) stored_rows += (a.rows.active[i] && a.rows.pslot[i] >= 0) ? 1 : 0;
+  const int nqt = grid.x, nt_all = a.nt1 + a.nt2;
+  const long base_ctas = (long)nqt * a.H * (stored_rows > 0 ? stored_rows : 1);
+  int ksplit = (int)((148L * 6 + base_ctas - 1) / base_ctas);
+  ksplit = ksplit < 1 ? 1 : (ksplit > nt_all ? nt_all : ksplit);
+  grid.x = nqt * ksplit;
+  kern<<<grid, kThreads, smem, st>>>(a, lse, nqt, ksplit);
+  IEF_LAUNCH_OK("attn_probs_from_lse_kernel");
+  return IEF_OK;
+}
+
+template <int DTYPE>
+int launch_probs_dp(const MmaArgs& a, const float* lse, dim3 grid, cudaStream_t st) {
+  const int d = a.d;
+  if (d <= 32) return launch_probs_one<DTYPE, 32>(a, lse, grid, st);
+  if (d <= 48) return launch_probs_one<DTYPE, 48>(a, lse, grid, st);
+  if (d <= 64) return launch_probs_one<DTYPE, 64>(a, lse, grid, st);
+  if (d <= 80) return launch_probs_one<DTYPE, 80>(a, lse, grid, st);
+  if (d <= 96) return launch_probs_one<DTYPE, 96>(a, lse, grid, st);
+  return launch_probs_one<DTYPE, 128>(a, lse, grid, st);
+}
+
 }  // namespace
 
 int ief_attn_mma_launch(const ief_attn_params* p, const IefRowTable& rows, cudaStream_t st) {
@@ -278,4 +404,23 @@ int ief_attn_mma_launch(const ief_attn_params* p, const IefRowTable& rows, cudaS
     return p->dtype == IEF_BF16 ? launch_dp<IEF_BF16, true>(a, grid, st) : launch_dp<IEF_F16, true>(a, grid, st);
   }
   return p->dtype == IEF_BF16 ? launch_dp<IEF_BF16, false>(a, grid, st) : launch_dp<IEF_F16, false>(a, grid, st);
+}
+
+// Stored maps behind a tcgen05 launch that produced O and the row log-sum-exp (log2 units, [B, H, Nq]): one QK^T sweep.
+int ief_attn_probs_from_lse_launch(const ief_attn_params* p, const IefRowTable& rows, const float* lse, cudaStream_t st) {
+  IEF_REQUIRE(p->d % 8 == 0 && p->d >= 8 && p->d <= 128, IEF_ERR_UNSUPPORTED, "ief_attn_fwd(probs from lse): head_dim %d", p->d);
+  MmaArgs a;
+  a.q = p->q; a.k = p->k; a.v = p->v; a.o = p->o;
+  a.B = p->B; a.H = p->H; a.Nq = p->Nq; a.Nk = p->Nk; a.d = p->d;
+  a.nt1 = ief_ceil_div(p->Nk, kBN);
+  bool any2 = false;
+  for (int i = 0; i < p->B; ++i) any2 |= rows.k2[i] >= 0;
+  a.nt2 = any2 ? a.nt1 : 0;
+  a.scale_log2 = p->scale * kLog2e;
+  a.probs = p->probs_out;
+  a.probs_accum = p->probs_accum;
+  a.key_bias = nullptr;
+  a.rows = rows;
+  dim3 grid(ief_ceil_div(p->Nq, kBM), p->H, p->B);
+  return p->dtype == IEF_BF16 ? launch_probs_dp<IEF_BF16>(a, lse, grid, st) : launch_probs_dp<IEF_F16>(a, lse, grid, st);
 }

@@ -364,8 +364,21 @@ static bool key_norm_prepass_pays(const ief_attn_params* p) {
          p->key_bias == nullptr && p->probs_out == nullptr;
 }
 
+// Stored maps (probs_out) of layers the tcgen05 kernels serve: O and the row log-sum-exp from them, then one QK^T sweep that writes
+// the maps (attn_probs_from_lse_kernel) — instead of the two-sweep mma.sync kernel. Needs B*H*Nq floats of workspace.
+bool ief_attn_probs_via_lse(const ief_attn_params* p) {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("IEF_PROBS_VIA_LSE"); on = (e && e[0] == '0') ? 0 : 1; }
+  if (!on || p->probs_out == nullptr || p->key_bias != nullptr || p->d > 128 || p->Nq < 512 || p->Nk < 256) return false;
+  ief_attn_params q = *p;
+  q.probs_out = nullptr;
+  return ief_attn_tc_supported(&q, nullptr);
+}
+
 extern "C" int64_t ief_attn_workspace_bytes(const ief_attn_params* p) {
-  if (p == nullptr || !key_norm_prepass_pays(p)) return 0;
+  if (p == nullptr) return 0;
+  if (ief_attn_probs_via_lse(p)) return (int64_t)p->B * p->H * p->Nq * (int64_t)sizeof(float);
+  if (!key_norm_prepass_pays(p)) return 0;
   return (int64_t)p->B * p->H * ief_ceil_div(p->Nk, 128) * (int64_t)sizeof(float);
 }
 
@@ -387,7 +400,7 @@ bool ief_attn_tc_supported(const ief_attn_params* p, const char** why) {
   return true;
 }
 
-int ief_attn_tc_launch(const ief_attn_params* p, const IefRowTable& rows, cudaStream_t st) {
+int ief_attn_tc_launch(const ief_attn_params* p, const IefRowTable& rows, cudaStream_t st, float* lse_out) {
   const char* why = "";
   IEF_REQUIRE(ief_attn_tc_supported(p, &why), IEF_ERR_UNSUPPORTED, "tcgen05 attention: %s", why);
   TcArgs a;
@@ -411,6 +424,7 @@ int ief_attn_tc_launch(const ief_attn_params* p, const IefRowTable& rows, cudaSt
   a.idesc_sum = make_idesc_f16(kBM, 16, fmt, 0, 0);
   a.knorm = nullptr;
   a.knorm_tiles = 0;
+  a.lse_out = lse_out;
   a.key_bias = nullptr;
   for (int i = 0; i < p->B; ++i)
     if (rows.bias[i] >= 0) a.key_bias = p->key_bias;
@@ -427,8 +441,11 @@ int ief_attn_tc_launch(const ief_attn_params* p, const IefRowTable& rows, cudaSt
   //   head_dim <= 64 : third generation (attn_tc3: column-split softmax, ordered exp sections), as 128-row split-KV CTAs when
   //                    that shortens the estimated wave time, else as 256-row CTAs; generation 2: attn_tc2s / attn_tc2
   //   head_dim <= 128: second generation (attn_tc2, P aliased onto S)        above: first generation (this file)
-  static int version = -1;
-  if (version < 0) { const char* e = getenv("IEF_TC_VERSION"); version = (e && e[0] >= '1' && e[0] <= '3') ? e[0] - '0' : 3; }
+  static int env_version = -1;
+  if (env_version < 0) { const char* e = getenv("IEF_TC_VERSION"); env_version = (e && e[0] >= '1' && e[0] <= '3') ? e[0] - '0' : 3; }
+  // a requested row log-sum-exp needs a generation whose epilogue writes it: 3 for head_dim <= 64, 2 (pair form) up to 128
+  const int version = lse_out != nullptr ? 3 : env_version;
+  IEF_REQUIRE(lse_out == nullptr || dch <= 2, IEF_ERR_UNSUPPORTED, "ief_attn_fwd: row log-sum-exp output needs head_dim <= 128");
   if (version >= 2 && dch == 1) {
     // 256-row CTAs (two query tiles share K/V) or 128-row CTAs (two key halves share Q)? Estimated time = waves x (key steps
     // per CTA + fixed prologue/epilogue, about three steps' worth): take the smaller. IEF_TC_SPLITKV=0|1|2 forces pair / split / hybrid.

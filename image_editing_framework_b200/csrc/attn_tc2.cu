@@ -347,6 +347,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tc_fence_after();
     const float inv = 1.f / l;
     const int grow = (2 * qt + t) * kBM + row;
+    if (a.lse_out != nullptr && grow < a.Nq) a.lse_out[((int64_t)b * a.H + h) * a.Nq + grow] = fmaf(m_used, c2, log2f(l));
     typename E::T* op = reinterpret_cast<typename E::T*>(a.o) + (int64_t)b * a.o_sb + (int64_t)grow * a.o_sn + (int64_t)h * a.o_sh;
     const int nchunk_d = (a.d + 15) >> 4;
     for (int cc = 0; cc < nchunk_d; ++cc) {

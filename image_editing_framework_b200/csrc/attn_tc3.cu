@@ -516,6 +516,12 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     }
     if (!SPLIT || t == 0) {
+      if (a.lse_out != nullptr && half == 0) {  // row log-sum-exp (log2 units) for the stored-maps sweep
+        const int r = (Cfg::kQTiles * qt + (SPLIT ? 0 : t)) * kBM + row;
+        // split flavour: lrow already is the merged sum relative to the joint maximum m_used + log2(1 / wmine) / c2
+        const float m_ref = (SPLIT && nt1 > 0) ? m_used * c2 - log2f(wmine) : m_used * c2;
+        if (r < a.Nq) a.lse_out[((int64_t)b * a.H + h) * a.Nq + r] = m_ref + log2f(lrow);
+      }
       const float inv = 1.f / lrow;
       wmine *= inv;
       wother *= inv;

@@ -88,5 +88,7 @@ static inline int ief_ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 // internal launchers (one per .cu)
 int ief_attn_mma_launch(const ief_attn_params* p, const IefRowTable& rows, cudaStream_t st);
-int ief_attn_tc_launch(const ief_attn_params* p, const IefRowTable& rows, cudaStream_t st);
+int ief_attn_tc_launch(const ief_attn_params* p, const IefRowTable& rows, cudaStream_t st, float* lse_out = nullptr);
+int ief_attn_probs_from_lse_launch(const ief_attn_params* p, const IefRowTable& rows, const float* lse, cudaStream_t st);
+bool ief_attn_probs_via_lse(const ief_attn_params* p);  // stored maps: tcgen05 (O + lse) followed by one QK^T sweep, given a workspace
 bool ief_attn_tc_supported(const ief_attn_params* p, const char** why);

@@ -94,10 +94,11 @@ typedef struct ief_attn_params {
                               variant of the tcgen05 kernel; no second K/V block. */
   const int32_t* bias_sel; /* HOST [B] or NULL (= no bias): row b uses key_bias[bias_sel[b]]; <0 = no bias for that row */
   int32_t n_bias;
-  void* workspace;         /* optional device scratch of >= ief_attn_workspace_bytes(p) bytes (16-byte aligned), or NULL. With it the
+  void* workspace;         /* optional device scratch of >= ief_attn_workspace_bytes(p) bytes (16-byte aligned), or NULL. With it (a) the
                               bf16 tcgen05 kernel runs a small pre-pass (max key norm per 128-key tile) whose Cauchy-Schwarz score
-                              bound lets most tiles skip the running-maximum pass; results are the same softmax. Contents are
-                              only meaningful during the call. */
+                              bound lets most tiles skip the running-maximum pass, (b) a call with probs_out on a layer the tcgen05
+                              kernels serve gets O and the row log-sum-exp from them and writes the maps in one further sweep
+                              instead of the two-sweep mma kernel. Same results either way; contents only live during the call. */
   int64_t workspace_bytes;
 } ief_attn_params;
 
