@@ -19,6 +19,8 @@ IEF_TC3_SKIPMAX=0 run tc_v3_no_skip "tcgen05 or fp16 or row_sources or masactrl 
 run cross "cross_attention"
 IEF_CROSS_TC=0 run cross_mma_only "cross_attention"
 run masked "key_bias or mask_blend"
+IEF_PROBS_VIA_LSE=0 run probs_two_sweep "probs_out"
+run backward "cross_attention_backward"
 run elem "ddim or accumulate or local_blend"
 echo "=== e2e"; timeout 900 python -m pytest tests/test_gpu_e2e.py -q -m gpu -p no:cacheprovider --timeout=600 > gpurun_out/t_e2e.log 2>&1; echo "exit $?"; tail -25 gpurun_out/t_e2e.log
 echo "=== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "exit $?"; tail -3 gpurun_out/smoke.log
