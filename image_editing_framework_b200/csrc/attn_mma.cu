@@ -323,7 +323,7 @@ attn_probs_from_lse_kernel(const __grid_constant__ MmaArgs a, const float* __res
           float* dst = a.probs + (prow + r) * nk_total + col0 + c;
           const float p0 = ief_exp2(fmaf(s[nb][2 * hh], c2, -ls)), p1 = ief_exp2(fmaf(s[nb][2 * hh + 1], c2, -ls));
           if (c + 1 < vc) {  // the pair as one 8-byte access (rows are 8-byte aligned when the key count is even)
-            if ((nk_total & 1) == 0) {
+            if (((nk_total | col0) & 1) == 0) {  // (second key block of an odd key count starts on an odd column)
               float2* d2 = reinterpret_cast<float2*>(dst);
               float2 old = a.probs_accum ? *d2 : make_float2(0.f, 0.f);
               *d2 = make_float2(old.x + p0, old.y + p1);

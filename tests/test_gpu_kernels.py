@@ -498,3 +498,22 @@ def test_cross_attention_backward(cuda, shape, with_dprobs):
     qf2 = q.float().clone().requires_grad_(True)
     (orc.apply_probs(orc.attention_probs(qf2, k.float(), H, scale), v.float(), H) * wo).sum().backward()
     assert (qd.grad.float().cpu() - qf2.grad).abs().max().item() <= 2e-2 * qf2.grad.abs().max().item() + 1e-3
+
+
+@pytest.mark.parametrize("accum", [False, True])
+def test_attn_probs_out_two_key_blocks_odd_key_count(cuda, accum):
+    """Stored maps of a call with a second key/value block and an ODD key count (the second block then starts on an odd column
+    of the map rows): found by tools/fuzz_attn.py as a misaligned 8-byte access in the log-sum-exp sweep."""
+    B, H, N, M, d = 2, 2, 640, 333, 64
+    q, k, v = _qkv(B, N, M, H, d, 23)
+    scale = d ** -0.5
+    kw = dict(k_src=[0, 0], v_src=[0, 0], k_src2=[0, 1], v_src2=[0, 1])
+    qh, kh = orc.head_to_batch(q.float(), H), orc.head_to_batch(torch.cat([k[[0, 0]], k[[0, 1]]], 1).float(), H)
+    want_p = (torch.bmm(qh, kh.transpose(1, 2)) * scale).softmax(-1)
+    want_o = orc.indexed_attention(q, k, v, H, scale, **kw)
+    probs = torch.full((B * H, N, 2 * M), 0.25 if accum else 7.0, device=cuda)
+    got = ops.attention(q.to(cuda), k.to(cuda), v.to(cuda), H, scale, probs_out=probs, probs_accum=accum, **kw)
+    torch.cuda.synchronize()
+    assert _cabi.last_attn_impl() == "tcgen05+probs"
+    assert (got.float().cpu() - want_o).abs().max().item() < TOL
+    assert (probs.cpu() - (0.25 if accum else 0.0) - want_p).abs().max().item() < 5e-3
