@@ -444,7 +444,8 @@ int ief_attn_tc_launch(const ief_attn_params* p, const IefRowTable& rows, cudaSt
   static int env_version = -1;
   if (env_version < 0) { const char* e = getenv("IEF_TC_VERSION"); env_version = (e && e[0] >= '1' && e[0] <= '3') ? e[0] - '0' : 3; }
   // a requested row log-sum-exp needs a generation whose epilogue writes it: 3 for head_dim <= 64, 2 (pair form) up to 128
-  const int version = lse_out != nullptr ? 3 : env_version;
+  // ... and a key bias is only implemented by generation 3
+  const int version = (lse_out != nullptr || a.key_bias != nullptr) ? 3 : env_version;
   IEF_REQUIRE(lse_out == nullptr || dch <= 2, IEF_ERR_UNSUPPORTED, "ief_attn_fwd: row log-sum-exp output needs head_dim <= 128");
   if (version >= 2 && dch == 1) {
     // 256-row CTAs (two query tiles share K/V) or 128-row CTAs (two key halves share Q)? Estimated time = waves x (key steps

@@ -76,7 +76,8 @@ for case in range(n_cases):
         perr = (probs - p_ref.reshape(B * H, N, -1)).abs().max().item() if probs is not None else 0.0
         worst = max(worst, err)
         tag = f"case {case}: dtype={dtype} B={B} H={H} N={N} M={M} d={d} scale={scale:.3f} src={q_src},{k_src},{v_src} k2={k2} bias={use_bias} probs={want_probs} impl={impl} -> {_cabi.last_attn_impl()}"
-        if not (err < TOL and perr < 1e-2) or not torch.isfinite(got).all():
+        tol = TOL * max(1.0, scale * d ** 0.5)   # the 2e-2 gate is stated for scale = d^-0.5; tripled logits triple the bf16 error
+        if not (err < tol and perr < 1e-2) or not torch.isfinite(got).all():
             print("FAIL", tag, "err", err, "probs err", perr)
             sys.exit(1)
 print(f"{n_cases} random cases ok, worst max-abs error {worst:.4f}")
