@@ -99,3 +99,32 @@ def test_random_masactrl_edit_matches_live_reference(monkeypatch, seed):
     got = editing.masactrl_edit(pipe, prompts, torch.cat([lat, lat]), steps, 7.5)
     assert mine.cur_step == ed.cur_step
     assert torch.allclose(got, want, atol=3e-4), (start_step, start_layer, layer_idx, (got - want).abs().max().item())
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_random_pnp_edit_matches_live_reference(monkeypatch, seed):
+    """Plug-and-Play with random step count and injection thresholds (incl. 0 and 1: nothing / everything injected)."""
+    ref = reference_loader.load_reference("pnp")
+    rng = random.Random(200 + seed)
+    steps = rng.choice([3, 4, 6])
+    attn_t, f_t = rng.choice([0.0, 0.34, 0.5, 1.0]), rng.choice([0.0, 0.5, 0.8, 1.0])
+    prompts = [" ".join(rng.choice(WORDS) for _ in range(4)) for _ in range(2)]
+    lat = torch.randn(1, 4, 8, 8, generator=torch.Generator().manual_seed(seed))
+    pipe = make_pipeline(tiny_config(), seed=seed)
+    pipe.scheduler.set_timesteps(steps)
+    ts = pipe.scheduler.timesteps
+    ref.register.register_attention_control_efficient(pipe, ts[:int(steps * attn_t)])
+    ref.register.register_conv_control_efficient(pipe, ts[:int(steps * f_t)])
+    context = _context(pipe, prompts)
+    latents = torch.cat([lat, lat])
+    with torch.no_grad():
+        for t in ts:
+            ref.register.register_time(pipe, t.item())
+            noise = pipe.unet(torch.cat([latents] * 2), t, encoder_hidden_states=context).sample
+            nu, nc = noise.chunk(2)
+            latents = pipe.scheduler.step(nu + 7.5 * (nc - nu), t, latents).prev_sample
+    want = latents.clone()
+    cpu_backend.install(monkeypatch)
+    pipe = make_pipeline(tiny_config(), seed=seed)
+    got = editing.pnp_edit(pipe, prompts, torch.cat([lat, lat]), steps, 7.5, pnp_attn_t=attn_t, pnp_f_t=f_t)
+    assert torch.allclose(got, want, atol=3e-4), (steps, attn_t, f_t, (got - want).abs().max().item())
