@@ -40,6 +40,21 @@ def test_struct_sizes_match_header_layout():
     assert C.sizeof(_cabi.CrossParams) == 128 + 32 + 8 + 8 + 8 + 7 * 8 + 8 + 8 + 8
 
 
+def test_integration_stub_matches_the_binding():
+    """The ctypes stub INTEGRATION.md shows a maintainer must lay its structs out exactly as the tested binding does."""
+    import ctypes as C
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    stub = re.search(r"```python\n(# p2p/model/_ief\.py.*?)```", doc, re.S).group(1)
+    stub = stub.replace('C.CDLL("libief_b200.so")', f'C.CDLL({_cabi.LIB_PATH!r})')
+    ns = {}
+    exec(compile(stub, "INTEGRATION.md", "exec"), ns)            # loads the library and checks the ABI number it quotes
+    for name, ours in (("Tensor4", _cabi.Tensor4), ("AttnParams", _cabi.AttnParams)):
+        theirs = ns[name]
+        assert C.sizeof(theirs) == C.sizeof(ours), name
+        assert [(f[0], getattr(theirs, f[0]).offset) for f in theirs._fields_] == \
+               [(f[0], getattr(ours, f[0]).offset) for f in ours._fields_], name
+
+
 def test_ops_refuse_cpu_tensors():
     from image_editing_framework_b200 import ops
     q = torch.zeros(1, 8, 16, dtype=torch.bfloat16)
