@@ -517,3 +517,25 @@ def test_attn_probs_out_two_key_blocks_odd_key_count(cuda, accum):
     assert _cabi.last_attn_impl() == "tcgen05+probs"
     assert (got.float().cpu() - want_o).abs().max().item() < TOL
     assert (probs.cpu() - (0.25 if accum else 0.0) - want_p).abs().max().item() < 5e-3
+
+
+# ---------------------------------------------------------------------------------------------------- the documented binding
+def test_integration_md_stub_runs_the_kernel(cuda):
+    """INTEGRATION.md §2's ctypes stub — the binding a reference maintainer would paste — drives ief_attn_fwd on its own and
+    reproduces MasaCtrl's mutual self-attention (masactrl/model/attention_control.py:51-58: targets read the sources' K/V)."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    stub = re.search(r"```python\n(# p2p/model/_ief\.py.*?)```", doc, re.S).group(1)
+    ns = {}
+    exec(compile(stub.replace('C.CDLL("libief_b200.so")', f'C.CDLL({_cabi.LIB_PATH!r})'), "INTEGRATION.md", "exec"), ns)
+    B, N, H, d = 4, 1024, 8, 40
+    q, k, v = _qkv(B, N, N, H, d, seed=77)
+    src = [0, 0, 2, 2]
+    before = _cabi.launch_count()
+    got = ns["attn_fwd"](q.to(cuda), k.to(cuda), v.to(cuda), H, d ** -0.5, k_src=src, v_src=src)
+    torch.cuda.synchronize()
+    assert _cabi.launch_count() > before
+    want = orc.indexed_attention(q, k, v, H, d ** -0.5, k_src=src, v_src=src)
+    assert (got.float().cpu() - want).abs().max().item() < TOL
