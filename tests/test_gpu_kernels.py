@@ -4,6 +4,7 @@ Tolerance: north_star states 2e-2 max-abs for bf16/fp16 attention outputs relati
 fp32-elementwise work (DDIM step, store accumulate) is checked bit-exact.
 """
 import math
+import os
 
 import pytest
 import torch
@@ -514,7 +515,8 @@ def test_attn_probs_out_two_key_blocks_odd_key_count(cuda, accum):
     probs = torch.full((B * H, N, 2 * M), 0.25 if accum else 7.0, device=cuda)
     got = ops.attention(q.to(cuda), k.to(cuda), v.to(cuda), H, scale, probs_out=probs, probs_accum=accum, **kw)
     torch.cuda.synchronize()
-    assert _cabi.last_attn_impl() == "tcgen05+probs"
+    if os.environ.get("IEF_PROBS_VIA_LSE", "1") != "0":      # the switch that sends stored maps back to the two-sweep mma kernel
+        assert _cabi.last_attn_impl() == "tcgen05+probs"
     assert (got.float().cpu() - want_o).abs().max().item() < TOL
     assert (probs.cpu() - (0.25 if accum else 0.0) - want_p).abs().max().item() < 5e-3
 

@@ -24,3 +24,11 @@ run backward "cross_attention_backward"
 run elem "ddim or accumulate or local_blend"
 echo "=== e2e"; timeout 900 python -m pytest tests/test_gpu_e2e.py -q -m gpu -p no:cacheprovider --timeout=600 > gpurun_out/t_e2e.log 2>&1; echo "exit $?"; tail -25 gpurun_out/t_e2e.log
 echo "=== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "exit $?"; tail -3 gpurun_out/smoke.log
+fuzz() { name=$1; shift; echo "=== fuzz $name"; for t in fuzz_attn fuzz_attn_rows; do timeout 300 python tools/$t.py 7 60 2> gpurun_out/f_${name}_$t.err | tail -2; echo "exit ${PIPESTATUS[0]}"; done; }
+fuzz default
+IEF_TC_VERSION=2 fuzz v2
+IEF_TC_SPLITKV=0 fuzz v3_pair
+IEF_TC_SPLITKV=1 fuzz v3_split
+IEF_TC3_SKIPMAX=2 fuzz skip_everywhere
+IEF_PROBS_VIA_LSE=0 fuzz probs_two_sweep
+IEF_TC3_NO_SUM_MMA=1 fuzz no_summma
