@@ -8,6 +8,7 @@ from __future__ import annotations
 
 from typing import List, Optional
 
+import numpy as np
 import torch
 
 from . import ops
@@ -68,15 +69,47 @@ class ddim_inversion:
         uncond = model.text_encoder(un.input_ids.to(model.device))[0]
         return torch.cat([uncond, cond])
 
+    def _invert(self, model, latent, unet_kwargs):
+        """The loop both classes share: the scheduler's timesteps walked backwards, one UNet forward + one fused reverse step each."""
+        trajectory = [latent]
+        latent = latent.clone().detach()
+        for t in reversed(model.scheduler.timesteps.tolist()):   # one host copy instead of a device sync per step
+            noise_pred = model.unet(latent, t, **unet_kwargs).sample
+            latent = self.ddim_reverse(model, noise_pred, t, latent)
+            trajectory.append(latent)
+        return trajectory
+
     @torch.no_grad()
     def ddim_inversion_loop(self, model, latent, prompt, cross_attention_kwargs=None):
         context = self.get_context(model, prompt)
         _, cond = context.chunk(2)
-        all_latent = [latent]
-        latent = latent.clone().detach()
-        steps = model.scheduler.timesteps.tolist()  # one host copy instead of a sync per step
-        for t in reversed(steps):
-            noise_pred = model.unet(latent, t, encoder_hidden_states=cond).sample
-            latent = self.ddim_reverse(model, noise_pred, t, latent)
-            all_latent.append(latent)
-        return all_latent, context
+        return self._invert(model, latent, dict(encoder_hidden_states=cond, cross_attention_kwargs=cross_attention_kwargs)), context
+
+    @torch.no_grad()
+    def image2latent(self, model, image, device, dtype):
+        """uint8 HWC image -> scaled VAE latent mean (*/inversion/ddim.py:35-41)."""
+        pixels = torch.as_tensor(np.asarray(image)).to(dtype).div(127.5).sub(1.0)
+        latents = model.vae.encode(pixels.permute(2, 0, 1)[None].to(device))["latent_dist"].mean
+        return latents * model.vae.config.scaling_factor
+
+
+class ddim_inversion_xl(ddim_inversion):
+    """SDXL flavour (*/inversion/ddim.py:60-109): the context is encode_prompt's 4-tuple and every forward carries the pooled text
+    embedding + size/crop ids as added_cond_kwargs. Only the conditional half is inverted, as in the SD-1.5 class."""
+
+    def get_context(self, model, prompt):
+        return tuple(model.encode_prompt(prompt=prompt, prompt_2=None, device=model.unet.device, num_images_per_prompt=1,
+                                         do_classifier_free_guidance=True, negative_prompt=None, negative_prompt_2=None,
+                                         prompt_embeds=None, negative_prompt_embeds=None, pooled_prompt_embeds=None,
+                                         negative_pooled_prompt_embeds=None, lora_scale=None))
+
+    @torch.no_grad()
+    def ddim_inversion_loop(self, model, latent, prompt, cross_attention_kwargs=None, height=1024, width=1024):
+        context = self.get_context(model, prompt)
+        prompt_embeds, _, pooled, _ = context
+        device = model._execution_device
+        size = (height, width)
+        time_ids = model._get_add_time_ids(size, (0, 0), size, dtype=prompt_embeds.dtype).to(device)
+        extra = {"text_embeds": pooled.to(device), "time_ids": time_ids}
+        return self._invert(model, latent, dict(encoder_hidden_states=prompt_embeds.to(device), cross_attention_kwargs=cross_attention_kwargs,
+                                                added_cond_kwargs=extra)), context

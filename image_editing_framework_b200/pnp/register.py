@@ -11,6 +11,8 @@ Here the copies are per-row source indices of ONE ief_attn_fwd launch. `t in inj
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from .. import ops
@@ -171,3 +173,11 @@ def register_time_xl(model, t):
                 setattr(tb.attn1, 't', t)
     for tb in model.unet.mid_block.attentions[0].transformer_blocks:
         setattr(tb.attn1, 't', t)
+
+
+def load_source_latents_t(t, latents_path):
+    """The inversion latent saved for timestep t as `noisy_latents_{t}.pt` (pnp/model/register.py:21-25)."""
+    path = os.path.join(latents_path, f"noisy_latents_{t}.pt")
+    if not os.path.exists(path):
+        raise FileNotFoundError(f"no inversion latent for timestep {t}: {path}")
+    return torch.load(path)

@@ -453,3 +453,65 @@ def test_lean_store_keeps_localblend_result(monkeypatch):
     kept = [m for key in ("down_cross", "up_cross", "mid_cross") for m in store[key] if m is not None]
     assert len(kept) == 5 and all(m.shape[1] == 256 for m in kept)
     assert [m is None for m in store["down_cross"]] == [True, True, False, False]
+
+
+# ------------------------------------------------------------------------------------------------ SDXL inversion, image2latent
+class _XLPipeline:
+    """The handful of StableDiffusionXLPipeline members */inversion/ddim.py:60-109 touches, over the stand-in UNet."""
+
+    def __init__(self):
+        self._p = make_pipeline(tiny_config(), seed=3)
+        self.unet, self.scheduler, self.vae = self._p.unet, self._p.scheduler, self._p.vae
+        self.seen = []
+        inner = self.unet.forward
+
+        def recording_forward(sample, timestep, encoder_hidden_states, cross_attention_kwargs=None, added_cond_kwargs=None, **kw):
+            self.seen.append((int(timestep), cross_attention_kwargs, added_cond_kwargs))
+            return inner(sample, timestep, encoder_hidden_states)
+        self.unet.forward = recording_forward
+
+    @property
+    def _execution_device(self):
+        return self.unet.device
+
+    def encode_prompt(self, prompt, device, **kw):
+        assert kw["do_classifier_free_guidance"] is True and kw["prompt_2"] is None and kw["num_images_per_prompt"] == 1
+        pe, ne = self._p.encode_prompt(prompt, device)
+        return pe, ne, pe.mean(1), ne.mean(1)
+
+    def _get_add_time_ids(self, original_size, crops, target_size, dtype):
+        return torch.tensor([list(original_size) + list(crops) + list(target_size)], dtype=dtype)
+
+
+def test_ddim_inversion_xl_and_image2latent(monkeypatch):
+    cpu_backend.install(monkeypatch)
+    from image_editing_framework_b200.ddim import ddim_inversion, ddim_inversion_xl
+    model = _XLPipeline()
+    model.scheduler.set_timesteps(6)
+    x0 = torch.randn(1, 4, 8, 8, generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        traj, ctx = ddim_inversion_xl().ddim_inversion_loop(model, x0, ["a cat on a table"], height=64, width=64)
+    steps = model.scheduler.timesteps.tolist()
+    assert len(traj) == 7 and len(ctx) == 4 and [s[0] for s in model.seen] == steps[::-1]
+    for _, cak, extra in model.seen:
+        assert cak is None and torch.equal(extra["text_embeds"], ctx[2]) and extra["time_ids"].tolist() == [[64, 64, 0, 0, 64, 64]]
+    # every hop is the reference's ddim_reverse closed form (inversion/ddim.py:9-18) on the UNet's prediction for the conditional prompt
+    ac, stride = model.scheduler.alphas_cumprod, 1000 // 6
+    with torch.no_grad():
+        for i, t in enumerate(reversed(steps)):
+            eps = model._p.unet(traj[i], t, encoder_hidden_states=ctx[0]).sample
+            cur = min(999, t - stride)
+            a_cur = ac[cur] if cur >= 0 else model.scheduler.final_alpha_cumprod
+            assert torch.allclose(traj[i + 1], orc.ddim_step(eps, traj[i], a_cur, ac[t]), atol=1e-6, rtol=1e-5)
+    if reference_loader.reference_available():
+        ref = reference_loader.load_reference("p2p").ddim
+        live = _XLPipeline()
+        live.scheduler.set_timesteps(6)
+        want, _ = ref.ddim_inversion_xl().ddim_inversion_loop(live, x0, ["a cat on a table"], height=64, width=64)
+        assert all(torch.allclose(a, b, atol=1e-5, rtol=1e-5) for a, b in zip(traj, want))
+    image = np.random.default_rng(0).integers(0, 256, (64, 64, 3), dtype=np.uint8)
+    z = ddim_inversion().image2latent(model, image, "cpu", torch.float32)
+    pix = torch.from_numpy(image).float() / 127.5 - 1
+    assert torch.allclose(z, model.vae.encode(pix.permute(2, 0, 1)[None])["latent_dist"].mean * model.vae.config.scaling_factor)
+    if reference_loader.reference_available():
+        assert torch.equal(z, ref.ddim_inversion().image2latent(model, image, "cpu", torch.float32))
