@@ -1,0 +1,85 @@
+"""Shared pieces of the pipeline-level drivers that mirror the reference's `*/model/sd_utils.py` classes.
+
+Every method directory of the reference carries its own copy of the same three things around its 50-step loop: the text
+conditioning ([uncond * n, cond * n], or SDXL's encode_prompt + pooled embedding + size ids), a classifier-free-guidance UNet
+forward followed by `scheduler.step`, and the VAE decode to uint8. Here they exist once; the step update is the fused
+ief_cfg_ddim_step launch (ddim.FusedDDIM) instead of the scheduler's ~10 elementwise kernels.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from .ddim import FusedDDIM
+
+
+def text_context(model, prompts: List[str], negative: str = "", with_uncond: bool = True, truncation: bool = True):
+    """(uncond [n, 77, C] or None, cond [n, 77, C]) from the pipeline's tokenizer + text encoder."""
+    tk = model.tokenizer
+    extra = {"truncation": True} if truncation else {}
+    ids = tk(prompts, padding="max_length", max_length=tk.model_max_length, return_tensors="pt", **extra).input_ids
+    device = model.unet.device
+    cond = model.text_encoder(ids.to(device))[0]
+    uncond = None
+    if with_uncond:
+        neg = tk([negative] * len(prompts), padding="max_length", max_length=ids.shape[-1], return_tensors="pt").input_ids
+        uncond = model.text_encoder(neg.to(device))[0]
+    return uncond, cond
+
+
+def sdxl_conditioning(model, prompt, device, do_classifier_free_guidance: bool, height: int, width: int,
+                      batch_size: int) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
+    """SDXL context + added_cond_kwargs as the reference's `encode_prompt_xl` builds them (p2p/model/sd_utils.py:184-221):
+    [negative; positive] prompt embeddings, the pooled embeddings the same way, and one (size, crop, target) id row per UNet row."""
+    pos, neg, pooled, neg_pooled = model.encode_prompt(
+        prompt=prompt, prompt_2=None, device=device, num_images_per_prompt=1, do_classifier_free_guidance=do_classifier_free_guidance,
+        negative_prompt=None, negative_prompt_2=None, prompt_embeds=None, negative_prompt_embeds=None, pooled_prompt_embeds=None,
+        negative_pooled_prompt_embeds=None, lora_scale=None)
+    size = (height, width)
+    ids = model._get_add_time_ids(size, (0, 0), size, dtype=pos.dtype)
+    if do_classifier_free_guidance:
+        pos, pooled, ids = torch.cat([neg, pos]), torch.cat([neg_pooled, pooled]), torch.cat([ids, ids])
+    return pos.to(device), {"text_embeds": pooled.to(device), "time_ids": ids.to(device).repeat(batch_size, 1)}
+
+
+def fused_scheduler(model) -> FusedDDIM:
+    """One FusedDDIM per (pipeline, scheduler): the alpha table is read to the host once."""
+    fused = getattr(model, "_ief_fused_ddim", None)
+    if fused is None or fused.scheduler is not model.scheduler:
+        fused = model._ief_fused_ddim = FusedDDIM(model.scheduler)
+    return fused
+
+
+def guided_step(model, latents: torch.Tensor, context: torch.Tensor, t, guidance_scale: float, unet_kwargs: Optional[dict] = None,
+                always_guide: bool = True) -> torch.Tensor:
+    """unet(cat[latents]*2) -> uncond + g (cond - uncond) -> DDIM step, the last two in one kernel launch.
+    `always_guide=False` follows the drivers that skip guidance when guidance_scale <= 1 (single forward, plain step)."""
+    fused = fused_scheduler(model)
+    t = int(t)
+    kw = unet_kwargs or {}
+    if always_guide or guidance_scale > 1.0:
+        eps = model.unet(torch.cat([latents] * 2), t, encoder_hidden_states=context, **kw)["sample"]
+        return fused.step(eps, t, latents, guidance_scale)
+    eps = model.unet(latents, t, encoder_hidden_states=context, **kw)["sample"]
+    return fused.step(eps, t, latents, None)
+
+
+@torch.no_grad()
+def decode_latents(vae, latents: torch.Tensor, return_type: str = "np"):
+    """VAE decode -> [0, 1] -> uint8 NHWC numpy (`latent2image` of every reference driver); 'pt' keeps the [0, 1] tensor."""
+    image = vae.decode(latents.detach() / vae.config.scaling_factor)["sample"]
+    image = (image / 2 + 0.5).clamp(0, 1)
+    if return_type == "pt":
+        return image
+    return (image.cpu().permute(0, 2, 3, 1).numpy() * 255).astype(np.uint8)
+
+
+def start_latent(model, latent: Optional[torch.Tensor], height: int, width: int, generator, batch_size: int):
+    """(x_T [1, C, h/8, w/8], x_T expanded over the prompt batch); a missing x_T is drawn on the host generator like randn_tensor."""
+    c = model.unet.config.in_channels
+    if latent is None:
+        latent = torch.randn((1, c, height // 8, width // 8), generator=generator, dtype=model.unet.dtype).to(model.unet.device)
+    latent = latent * model.scheduler.init_noise_sigma
+    return latent, latent.expand(batch_size, c, height // 8, width // 8)

@@ -1,0 +1,83 @@
+"""Pipeline-level drivers (the classes of the reference's `*/model/sd_utils.py`) against the LIVE reference on the CPU stand-in
+(only where /root/reference is mounted; skipped elsewhere): the reference's class + its own register closures and scheduler versus
+this repository's class of the same name on oracle-backed ops. Images must agree to one uint8 step, start latents exactly."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import reference_loader
+from oracle import cpu_ops as cpu_backend
+from image_editing_framework_b200 import p2p
+from image_editing_framework_b200.standin import make_pipeline, tiny_config
+
+pytestmark = pytest.mark.skipif(not reference_loader.reference_available(), reason="reference tree not mounted")
+CPU = torch.device("cpu")
+PROMPTS = ["a photo of a cat sitting on the bench", "a photo of a dog sitting on the bench"]
+
+
+class _XL:
+    """StableDiffusionXLPipeline members the XL drivers touch, over the stand-in pipeline (added_cond_kwargs are recorded, the
+    stand-in UNet has no add-embedding)."""
+
+    def __init__(self, seed):
+        self._p = make_pipeline(tiny_config(), seed=seed)
+        for name in ("unet", "scheduler", "vae", "tokenizer", "text_encoder"):
+            setattr(self, name, getattr(self._p, name))
+        self.added = []
+        inner = self.unet.forward
+
+        def forward(sample, timestep, encoder_hidden_states, cross_attention_kwargs=None, added_cond_kwargs=None, **kw):
+            self.added.append(added_cond_kwargs)
+            return inner(sample, timestep, encoder_hidden_states)
+        self.unet.forward = forward
+
+    device = _execution_device = property(lambda self: self.unet.device)
+
+    def encode_prompt(self, prompt, device, do_classifier_free_guidance=True, **kw):
+        pe, ne = self._p.encode_prompt(prompt, device)
+        return pe, ne, pe.mean(1), ne.mean(1)
+
+    def _get_add_time_ids(self, original_size, crops, target_size, dtype):
+        return torch.tensor([list(original_size) + list(crops) + list(target_size)], dtype=dtype)
+
+
+def _controller(mod, tok, steps):
+    return mod.AttentionReplace(prompts=PROMPTS, tokenizer=tok, num_steps=steps, cross_replace_steps=0.8, self_replace_steps=0.5, device=CPU)
+
+
+def _null_text(steps, seed):
+    g = torch.Generator().manual_seed(seed)
+    return [torch.randn(1, 77, tiny_config().cross_attention_dim, generator=g) * 0.1 for _ in range(steps)]
+
+
+@pytest.mark.parametrize("name", ["P2P", "P2P_NTI", "P2P_XL", "P2P_XL_NTI"])
+def test_p2p_pipeline_classes_match_live_reference(monkeypatch, name):
+    ref = reference_loader.load_reference("p2p")
+    steps, xl, nti = 4, "XL" in name, "NTI" in name
+    lat = torch.randn(1, 4, 8, 8, generator=torch.Generator().manual_seed(11))
+    kw = {"uncond_embeddings_list": _null_text(steps, 12)} if nti else {}
+
+    def run(cls, ac_mod, pipe):
+        ctrl = _controller(ac_mod, pipe.tokenizer, steps)
+        editor = cls(pipe, steps)
+        # both sides hard-code 512^2 / 1024^2: keep their loop but start from an 8x8 latent so the CPU run stays small
+        editor.init_latent = lambda latent, model, h, w, gen, bs: (latent, latent.expand(bs, 4, 8, 8))
+        image, x_t = editor.text2image_ldm_stable(pipe, PROMPTS, ctrl, num_inference_steps=steps, guidance_scale=7.5, latent=lat, **kw)
+        return image, x_t, ctrl
+
+    want_img, want_xt, ref_ctrl = run(getattr(ref.sd_utils, name), ref.attention_control, _XL(7) if xl else make_pipeline(tiny_config(), seed=7))
+    cpu_backend.install(monkeypatch)
+    mine = _XL(7) if xl else make_pipeline(tiny_config(), seed=7)
+    got_img, got_xt, ctrl = run(getattr(p2p, name), p2p, mine)
+    assert got_img.dtype == np.uint8 and got_img.shape == want_img.shape
+    assert torch.equal(got_xt, want_xt) and ctrl.cur_step == ref_ctrl.cur_step == steps
+    assert np.abs(got_img.astype(np.int16) - want_img.astype(np.int16)).max() <= 1
+    if xl:
+        assert len(mine.added) == steps and all(a["time_ids"].shape == (2 * len(PROMPTS), 6) for a in mine.added)
+
+
+def test_p2p_pipeline_refuses_low_resource(monkeypatch):
+    cpu_backend.install(monkeypatch)
+    pipe = make_pipeline(tiny_config(), seed=1)
+    with pytest.raises(NotImplementedError, match="low_resource"):
+        p2p.P2P(pipe, 2).text2image_ldm_stable(pipe, PROMPTS, None, num_inference_steps=2, latent=torch.zeros(1, 4, 64, 64), low_resource=True)
