@@ -2,3 +2,4 @@ from .register import regiter_attention_editor_diffusers, unregister_attention_c
 from .attention_base import AttentionBase, AttentionStore
 from .attention_control import (MutualSelfAttentionControl, MutualSelfAttentionControlUnion, MutualSelfAttentionControlMask,
                                 MutualSelfAttentionControlMaskAuto)
+from .sd_utils import MasaCtrl, MasaCtrl_XL, MasaCtrl_NTI, MasaCtrl_XL_NTI

@@ -81,3 +81,40 @@ def test_p2p_pipeline_refuses_low_resource(monkeypatch):
     pipe = make_pipeline(tiny_config(), seed=1)
     with pytest.raises(NotImplementedError, match="low_resource"):
         p2p.P2P(pipe, 2).text2image_ldm_stable(pipe, PROMPTS, None, num_inference_steps=2, latent=torch.zeros(1, 4, 64, 64), low_resource=True)
+
+
+@pytest.mark.parametrize("name", ["MasaCtrl", "MasaCtrl_NTI", "MasaCtrl_XL", "MasaCtrl_XL_NTI"])
+@pytest.mark.parametrize("guidance", [7.5, 1.0])
+def test_masactrl_pipeline_classes_match_live_reference(monkeypatch, name, guidance):
+    from image_editing_framework_b200 import masactrl
+    ref = reference_loader.load_reference("masactrl")
+    steps, xl, nti = 4, "XL" in name, "NTI" in name
+    if (nti or xl) and guidance <= 1.0:
+        pytest.skip("without guidance the reference's NTI samplers pair a doubled context with an un-doubled batch and its XL "
+                    "encode_prompt_xl raises UnboundLocalError: nothing to compare with")
+    g = torch.Generator().manual_seed(21)
+    lat = torch.randn(1, 4, 8, 8, generator=g)
+    trajectory = [torch.randn(1, 4, 8, 8, generator=g) for _ in range(steps + 1)]      # stands for the DDIM inversion's latents
+    null = _null_text(steps, 22)
+
+    def run(cls, mod, pipe):
+        editor = mod.attention_control.MutualSelfAttentionControl(1, 10, total_steps=steps) if hasattr(mod, "attention_control") else \
+            mod.MutualSelfAttentionControl(1, 10, total_steps=steps)
+        (mod.register if hasattr(mod, "register") and hasattr(mod.register, "regiter_attention_editor_diffusers") else mod) \
+            .regiter_attention_editor_diffusers(pipe, editor)
+        kw = dict(height=64, width=64, num_inference_steps=steps, guidance_scale=guidance, latents=torch.cat([lat, lat]),
+                  ref_intermediate_latents=trajectory)
+        if nti:
+            kw["uncond_embeddings_list"] = null
+        elif not xl:
+            kw["unconditioning"] = null if guidance > 1.0 else None
+            kw["neg_prompt"] = "blurry"
+        image, x_t = cls(pipe, steps)(PROMPTS, **kw)
+        return image, x_t, editor
+
+    mk = (lambda: _XL(9)) if xl else (lambda: make_pipeline(tiny_config(), seed=9))
+    want_img, want_xt, ref_ed = run(getattr(ref.sd_utils, name), ref, mk())
+    cpu_backend.install(monkeypatch)
+    got_img, got_xt, ed = run(getattr(masactrl, name), masactrl, mk())
+    assert torch.equal(got_xt, want_xt) and ed.cur_step == ref_ed.cur_step == steps
+    assert got_img.shape == want_img.shape and np.abs(got_img.astype(np.int16) - want_img.astype(np.int16)).max() <= 1
