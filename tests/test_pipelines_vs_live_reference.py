@@ -9,6 +9,7 @@ from oracle import reference_loader
 from oracle import cpu_ops as cpu_backend
 from image_editing_framework_b200 import p2p
 from image_editing_framework_b200.standin import make_pipeline, tiny_config
+from image_editing_framework_b200.standin.unet import UNetConfig
 
 pytestmark = pytest.mark.skipif(not reference_loader.reference_available(), reason="reference tree not mounted")
 CPU = torch.device("cpu")
@@ -19,8 +20,8 @@ class _XL:
     """StableDiffusionXLPipeline members the XL drivers touch, over the stand-in pipeline (added_cond_kwargs are recorded, the
     stand-in UNet has no add-embedding)."""
 
-    def __init__(self, seed):
-        self._p = make_pipeline(tiny_config(), seed=seed)
+    def __init__(self, seed, config=None):
+        self._p = make_pipeline(config or tiny_config(), seed=seed)
         for name in ("unet", "scheduler", "vae", "tokenizer", "text_encoder"):
             setattr(self, name, getattr(self._p, name))
         self.added = []
@@ -32,6 +33,9 @@ class _XL:
         self.unet.forward = forward
 
     device = _execution_device = property(lambda self: self.unet.device)
+
+    def __getattr__(self, name):             # prepare_latents, progress_bar, vae_scale_factor, ... come from the stand-in pipeline
+        return getattr(self.__dict__["_p"], name)
 
     def encode_prompt(self, prompt, device, do_classifier_free_guidance=True, **kw):
         pe, ne = self._p.encode_prompt(prompt, device)
@@ -118,3 +122,26 @@ def test_masactrl_pipeline_classes_match_live_reference(monkeypatch, name, guida
     got_img, got_xt, ed = run(getattr(masactrl, name), masactrl, mk())
     assert torch.equal(got_xt, want_xt) and ed.cur_step == ref_ed.cur_step == steps
     assert got_img.shape == want_img.shape and np.abs(got_img.astype(np.int16) - want_img.astype(np.int16)).max() <= 1
+
+
+@pytest.mark.parametrize("name", ["PnP", "PnP_NTI", "PnP_XL", "PnP_XL_NTI"])
+def test_pnp_pipeline_classes_match_live_reference(monkeypatch, name):
+    from image_editing_framework_b200 import pnp
+    ref = reference_loader.load_reference("pnp")
+    steps, xl, nti = 5, "XL" in name, "NTI" in name
+    lat = torch.randn(1, 4, 8, 8, generator=torch.Generator().manual_seed(31))
+    kw = {"uncond_embeddings_list": _null_text(steps, 32)} if nti else {}
+
+    def run(cls, pipe):
+        return cls(pipe, steps)(PROMPTS, height=64, width=64, num_inference_steps=steps, guidance_scale=7.5, latents=lat,
+                                pnp_attn_t=0.5, pnp_f_t=0.8, **kw), pipe
+
+    # the *_xl hook tables address SDXL's block topology (3 blocks, no attention in the first): a tiny UNet of that shape
+    xl_cfg = UNetConfig(sample_size=8, block_out_channels=(32, 64, 64), transformer_layers=(0, 2, 3), num_heads=(2, 2, 2),
+                        cross_attention_dim=32, norm_num_groups=8, use_linear_projection=True, name="tiny_xl")
+    mk = (lambda: _XL(13, xl_cfg)) if xl else (lambda: make_pipeline(tiny_config(), seed=13))
+    want, ref_pipe = run(getattr(ref.sd_utils, name), mk())
+    cpu_backend.install(monkeypatch)
+    got, pipe = run(getattr(pnp, name), mk())
+    assert got.dtype == np.uint8 and got.shape == want.shape == (2, 64, 64, 3)
+    assert np.abs(got.astype(np.int16) - want.astype(np.int16)).max() <= 1
