@@ -120,7 +120,8 @@ def _cross_modules(unet):
 
 def pix2pix_zero_edit(model, embeds_src: torch.Tensor, embeds_edit: torch.Tensor, latents: torch.Tensor, num_inference_steps: int = 50,
                       guidance_scale: float = 7.5, guidance_amount: float = 0.1, only_sample: bool = False, graphs: bool = False,
-                      map_dtype: torch.dtype = torch.float32):
+                      map_dtype: torch.dtype = torch.float32, uncond_embeddings_list=None, unet_kwargs_src: Optional[dict] = None,
+                      unet_kwargs_edit: Optional[dict] = None):
     """Pix2Pix-zero's two denoising loops on latents (pix2pix-zero/model/sd_utils.py:86-182). The UNet must carry MyAttnProcessor
     (prep_unet). embeds_*: [uncond, cond] context pairs ([2, 77, C]); latents: [1, 4, h, w]. Returns (reconstruction latents,
     edited latents).
@@ -128,7 +129,13 @@ def pix2pix_zero_edit(model, embeds_src: torch.Tensor, embeds_edit: torch.Tensor
     Differences from the reference, none of them arithmetic: the reference cross-attention maps of loop 1 stay on the device
     (the reference moves 16 maps per step to the host with a blocking `.cpu()` and back in loop 2, :105-110,169); loop 1 and the
     recomputed-noise pass of loop 2 run the fused kernels (optionally replayed from a CUDA graph); only the guidance pass, which
-    needs d loss / d latents, runs differentiable torch arithmetic."""
+    needs d loss / d latents, runs differentiable torch arithmetic.
+
+    `uncond_embeddings_list[i]` (null-text inversion) overwrites row 0 of both contexts at step i (P2P_Zero_NTI, :518,:582);
+    `unet_kwargs_*` are extra UNet keyword arguments of the two loops (SDXL's added_cond_kwargs), which rule out graph replay."""
+    kw_src, kw_edit = unet_kwargs_src or {}, unet_kwargs_edit or {}
+    if graphs and (kw_src or kw_edit):
+        raise ValueError("pix2pix_zero_edit: graph replay covers unet(x, t, context) only; drop graphs=True when passing UNet kwargs")
     model.scheduler.set_timesteps(num_inference_steps)
     fused = FusedDDIM(model.scheduler)
     ts = model.scheduler.timesteps.tolist()
@@ -137,9 +144,11 @@ def pix2pix_zero_edit(model, embeds_src: torch.Tensor, embeds_edit: torch.Tensor
     runner = GraphedUNet(model.unet, None, None, launch_counter=_cabi.launch_count) if graphs else None
     ref_maps = {}
     with torch.no_grad():  # loop 1: reference maps (:92-122)
-        for t in ts:
+        for i, t in enumerate(ts):
+            if uncond_embeddings_list is not None:
+                embeds_src[0] = uncond_embeddings_list[i]
             x = torch.cat([latents] * 2)
-            eps = runner(x, t, embeds_src) if runner is not None else model.unet(x, t, encoder_hidden_states=embeds_src)["sample"]
+            eps = runner(x, t, embeds_src) if runner is not None else model.unet(x, t, encoder_hidden_states=embeds_src, **kw_src)["sample"]
             # a replayed graph rewrites the same attn_probs buffers every step: the cache must own its copy either way
             ref_maps[t] = [m.attn_probs.detach().to(map_dtype, copy=True) for _, m in cross]
             latents = fused.step(eps, t, latents, guidance_scale)
@@ -149,17 +158,20 @@ def pix2pix_zero_edit(model, embeds_src: torch.Tensor, embeds_edit: torch.Tensor
             runner.close()
         return latents_rec, None
     latents = latents_init
-    for t in ts:  # loop 2: cross-attention guidance (:152-182)
+    for i, t in enumerate(ts):  # loop 2: cross-attention guidance (:152-182)
+        if uncond_embeddings_list is not None:
+            embeds_edit[0] = uncond_embeddings_list[i]
         x_in = torch.cat([latents] * 2).detach().clone().requires_grad_(True)
         with torch.enable_grad():
-            model.unet(x_in, t, encoder_hidden_states=embeds_edit.detach())
+            model.unet(x_in, t, encoder_hidden_states=embeds_edit.detach(), **kw_edit)
             loss = 0.0
             for (_, m), ref in zip(cross, ref_maps[t]):
                 loss = loss + ((m.attn_probs.float() - ref.float()) ** 2).sum((1, 2)).mean(0)
             grad, = torch.autograd.grad(loss, x_in)
         with torch.no_grad():
             x_new = (x_in - guidance_amount * grad).detach()   # torch.optim.SGD([x_in], lr=guidance_amount).step()
-            eps = runner(x_new, t, embeds_edit) if runner is not None else model.unet(x_new, t, encoder_hidden_states=embeds_edit)["sample"]
+            eps = runner(x_new, t, embeds_edit) if runner is not None else \
+                model.unet(x_new, t, encoder_hidden_states=embeds_edit, **kw_edit)["sample"]
             latents = x_new.chunk(2)[0]
             latents = fused.step(eps, t, latents, guidance_scale)
     if runner is not None:

@@ -53,7 +53,7 @@ _MODULES = {
     "p2p": ["ptp_utils", "seq_aligner", "attention_base", "attention_control", "register", "sd_utils"],
     "masactrl": ["attention_base", "attention_control", "register", "sd_utils"],
     "pnp": ["register", "sd_utils"],
-    "pix2pix-zero": ["attention_control"],
+    "pix2pix-zero": ["attention_control", "sd_utils"],
 }
 
 

@@ -466,8 +466,19 @@ def gen_ddim():
     _save("ddim.pt", dict(seed=6, reverse=rev, forward=fwd, guidance=7.5, timesteps=sch.timesteps.clone(), alphas_cumprod=sch.alphas_cumprod.clone()))
 
 
+def gen_pipelines():
+    """uint8 images of the 16 pipeline-level classes (`*/model/sd_utils.py`) on the scenarios of tests/scenarios.py."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import scenarios
+    out = {}
+    for family, name in scenarios.PIPELINE_CASES:
+        images, _ = scenarios.run_pipeline_case(family, name, load_reference(family), CPU)
+        out[name] = [torch.from_numpy(im.copy()) for im in images]
+    _save("pipelines.pt", out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["aligner", "oracle_pins", "ddim", "p2p", "masactrl", "pnp", "pnp_xl", "pix2pix_zero", "p2p_localblend", "masactrl_masks", "pix2pix_zero_loop"]
+    which = sys.argv[1:] or ["aligner", "oracle_pins", "ddim", "p2p", "masactrl", "pnp", "pnp_xl", "pix2pix_zero", "p2p_localblend", "masactrl_masks", "pix2pix_zero_loop", "pipelines"]
     for w in which:
         globals()["gen_" + w]()

@@ -198,3 +198,104 @@ def run_p2p_localblend(g, device, lean_store=False):
             per_step.append(latents.float().cpu())
     maps = ctrl.attention_store["down_cross"][2:4] + ctrl.attention_store["up_cross"][:3]
     return ctrl, per_step, [m.float().cpu() for m in maps]
+
+
+# --------------------------------------------------------------------------------- pipeline-level classes (`*/model/sd_utils.py`)
+PIPELINE_PROMPTS = ["a photo of a cat sitting on the bench", "a photo of a dog sitting on the bench"]
+PIPELINE_CASES = [(family, base + suffix) for family, base in (("p2p", "P2P"), ("masactrl", "MasaCtrl"), ("pnp", "PnP"), ("pix2pix-zero", "P2P_Zero"))
+                  for suffix in ("", "_NTI", "_XL", "_XL_NTI")]
+TINY_XL = dict(sample_size=8, block_out_channels=(32, 64, 64), transformer_layers=(0, 2, 3), num_heads=(2, 2, 2),
+               cross_attention_dim=32, norm_num_groups=8, use_linear_projection=True, name="tiny_xl")
+
+
+class XLPipelineDouble:
+    """The StableDiffusionXLPipeline members the XL drivers touch, over the stand-in pipeline. added_cond_kwargs are recorded (the
+    stand-in UNet has no add-embedding); the pooled embedding is the token mean."""
+
+    def __init__(self, seed, config, device):
+        self._p = make_pipeline(config, seed=seed, device=device)
+        for name in ("unet", "scheduler", "vae", "tokenizer", "text_encoder"):
+            setattr(self, name, getattr(self._p, name))
+        self.added = []
+        inner = self.unet.forward
+
+        def forward(sample, timestep, encoder_hidden_states, cross_attention_kwargs=None, added_cond_kwargs=None, **kw):
+            self.added.append(added_cond_kwargs)
+            return inner(sample, timestep, encoder_hidden_states)
+        self.unet.forward = forward
+
+    device = _execution_device = property(lambda self: self.unet.device)
+
+    def __getattr__(self, name):             # prepare_latents, progress_bar, vae_scale_factor, ... come from the stand-in pipeline
+        return getattr(self.__dict__["_p"], name)
+
+    def encode_prompt(self, prompt, device, do_classifier_free_guidance=True, **kw):
+        pe, ne = self._p.encode_prompt(prompt, device)
+        return pe, ne, pe.mean(1), ne.mean(1)
+
+    def _get_add_time_ids(self, original_size, crops, target_size, dtype):
+        return torch.tensor([list(original_size) + list(crops) + list(target_size)], dtype=dtype)
+
+
+def null_text_embeddings(steps, seed, device, dim=32):
+    g = torch.Generator().manual_seed(seed)
+    return [(torch.randn(1, 77, dim, generator=g) * 0.1).to(device) for _ in range(steps)]
+
+
+def run_pipeline_case(family, name, api, device):
+    """One fixed scenario per pipeline-level class, written against `api` = the reference's modules of that family
+    (oracle.reference_loader) or this package's mirror of them — the class and hook names are the same on both sides.
+    Returns the uint8 images the class produces (a list) and the pipeline it ran on."""
+    xl, nti = "XL" in name, "NTI" in name
+    # the *_xl PnP hook tables address SDXL's block topology (3 blocks, no attention in the first)
+    cfg = UNetConfig(**TINY_XL) if (xl and family == "pnp") else tiny_config()
+    seed = {"p2p": 7, "masactrl": 9, "pnp": 13, "pix2pix-zero": 17}[family]
+    pipe = XLPipelineDouble(seed, cfg, device) if xl else make_pipeline(cfg, seed=seed, device=device)
+    g = torch.Generator().manual_seed(100 + seed)
+    lat = torch.randn(1, 4, 8, 8, generator=g).to(device)
+    cls = getattr(api.sd_utils, name)
+    if family == "p2p":
+        steps = 4
+        ctrl = api.attention_control.AttentionReplace(prompts=PIPELINE_PROMPTS, tokenizer=pipe.tokenizer, num_steps=steps,
+                                                      cross_replace_steps=0.8, self_replace_steps=0.5, device=device)
+        editor = cls(pipe, steps)
+        # both sides hard-code 512^2 / 1024^2: keep their loop but start from an 8x8 latent so a CPU run stays small
+        editor.init_latent = lambda latent, model, h, w, gen, bs: (latent, latent.expand(bs, 4, 8, 8))
+        kw = {"uncond_embeddings_list": null_text_embeddings(steps, 12, device)} if nti else {}
+        image, x_t = editor.text2image_ldm_stable(pipe, PIPELINE_PROMPTS, ctrl, num_inference_steps=steps, guidance_scale=7.5, latent=lat, **kw)
+        assert ctrl.cur_step == steps and torch.equal(x_t, lat)
+        return [image], pipe
+    if family == "masactrl":
+        steps = 4
+        trajectory = [torch.randn(1, 4, 8, 8, generator=g).to(device) for _ in range(steps + 1)]   # stands for the inversion's latents
+        editor = api.attention_control.MutualSelfAttentionControl(1, 10, total_steps=steps)
+        api.register.regiter_attention_editor_diffusers(pipe, editor)
+        kw = dict(height=64, width=64, num_inference_steps=steps, guidance_scale=7.5, latents=torch.cat([lat, lat]),
+                  ref_intermediate_latents=trajectory)
+        if nti:
+            kw["uncond_embeddings_list"] = null_text_embeddings(steps, 22, device)
+        elif not xl:
+            kw.update(unconditioning=null_text_embeddings(steps, 22, device), neg_prompt="blurry")
+        image, x_t = cls(pipe, steps)(PIPELINE_PROMPTS, **kw)
+        assert editor.cur_step == steps and torch.equal(x_t, torch.cat([lat, lat]))
+        return [image], pipe
+    if family == "pnp":
+        steps = 5
+        kw = {"uncond_embeddings_list": null_text_embeddings(steps, 32, device)} if nti else {}
+        image = cls(pipe, steps)(PIPELINE_PROMPTS, height=64, width=64, num_inference_steps=steps, guidance_scale=7.5, latents=lat,
+                                 pnp_attn_t=0.5, pnp_f_t=0.8, **kw)
+        return [image], pipe
+    steps = 3
+    edit_dir = (torch.randn(1, 77, 32, generator=g) * 0.05).to(device)
+    kw = {"uncond_embeddings_list": null_text_embeddings(steps, 42, device)} if nti else {}
+    rec, edit = cls(pipe, steps)(PIPELINE_PROMPTS, height=64, width=64, num_inference_steps=steps, guidance_scale=7.5, latents=lat.clone(),
+                                 guidance_amount=0.1, edit_dir=edit_dir, **kw)
+    return [rec, edit], pipe
+
+
+def mirror_api(family):
+    """This package's modules under the attribute names the reference's `model` package uses."""
+    from types import SimpleNamespace
+    import image_editing_framework_b200 as pkg
+    mod = {"p2p": pkg.p2p, "masactrl": pkg.masactrl, "pnp": pkg.pnp, "pix2pix-zero": pkg.pix2pix_zero}[family]
+    return SimpleNamespace(sd_utils=mod, attention_control=mod, register=mod)

@@ -299,3 +299,16 @@ def test_graph_runner_falls_back_to_eager_for_unreplayable_controllers(cuda):
         assert ed.cur_step == 4 and ed.valid_steps == 4 and len(ed.self_attns) > 0
     assert stats["replays"] == 0 and stats["eager_calls"] == 4
     assert psnr(outs[1], outs[0]) >= 60.0
+
+
+@pytest.mark.parametrize("family,name", scenarios.PIPELINE_CASES)
+def test_pipeline_classes_match_reference_images(cuda, family, name):
+    """The pipeline-level classes with the reference's names (`*/model/sd_utils.py`: text conditioning -> controlled denoising loop
+    -> VAE decode) on the GPU through the CUDA kernels, against the uint8 images the reference's classes produced (CPU fp32)."""
+    want = golden("pipelines.pt")[name]
+    before = _cabi.launch_count()
+    got, _ = scenarios.run_pipeline_case(family, name, scenarios.mirror_api(family), cuda)
+    assert _cabi.launch_count() - before >= 3 * 32, "the denoising loop did not go through libief_b200"
+    for a, b in zip(got, want):
+        db = psnr(torch.from_numpy(a).float() / 255, b.float() / 255)
+        assert db >= PSNR_DB, f"{name}: image PSNR {db:.1f} dB"

@@ -515,3 +515,16 @@ def test_ddim_inversion_xl_and_image2latent(monkeypatch):
     assert torch.allclose(z, model.vae.encode(pix.permute(2, 0, 1)[None])["latent_dist"].mean * model.vae.config.scaling_factor)
     if reference_loader.reference_available():
         assert torch.equal(z, ref.ddim_inversion().image2latent(model, image, "cpu", torch.float32))
+
+
+# ------------------------------------------------------------------------------------------------ pipeline-level classes
+@pytest.mark.parametrize("family,name", scenarios.PIPELINE_CASES)
+def test_pipeline_classes_reproduce_reference_images(monkeypatch, family, name):
+    """P2P / MasaCtrl / PnP / P2P_Zero and their _XL / _NTI variants (`*/model/sd_utils.py`) against images the reference's own
+    classes produced on the same stand-in (tests/golden/pipelines.pt): host logic of the mirrors on oracle-backed ops."""
+    cpu_backend.install(monkeypatch)
+    want = golden("pipelines.pt")[name]
+    got, _ = scenarios.run_pipeline_case(family, name, scenarios.mirror_api(family), torch.device("cpu"))
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert a.dtype == np.uint8 and np.abs(a.astype(np.int16) - b.numpy().astype(np.int16)).max() <= 1
