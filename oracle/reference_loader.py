@@ -58,7 +58,7 @@ _MODULES = {
 
 
 def load_reference(method: str) -> SimpleNamespace:
-    """Namespace with the reference's `model.<name>` modules of one method plus `ddim` (= inversion.ddim)."""
+    """Namespace with the reference's `model.<name>` modules of one method plus `ddim` / `nti` (= inversion.ddim / inversion.nti)."""
     if method in _CACHE:
         return _CACHE[method]
     if not reference_available():
@@ -75,6 +75,7 @@ def load_reference(method: str) -> SimpleNamespace:
         for name in _MODULES[method]:
             ns[name] = importlib.import_module(f"model.{name}")
         ns["ddim"] = importlib.import_module("inversion.ddim")
+        ns["nti"] = importlib.import_module("inversion.nti")
     finally:
         sys.dont_write_bytecode = old
         sys.path.remove(root)

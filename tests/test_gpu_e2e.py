@@ -313,3 +313,31 @@ def test_pipeline_classes_match_reference_images(cuda, family, name):
     for a, b in zip(got, want):
         db = psnr(torch.from_numpy(a).float() / 255, b.float() / 255)
         assert db >= PSNR_DB, f"{name}: image PSNR {db:.1f} dB"
+
+
+def test_null_text_inversion_runs_on_the_fused_step(cuda):
+    """*/inversion/nti.py on the GPU: DDIM inversion (fused reverse step) and the null-text search, whose latent advances through the
+    fused guided step; replaying the found embeddings with P2P_NTI must reconstruct the inverted latent better than the plain "" prompt."""
+    from image_editing_framework_b200 import nti, p2p
+    from image_editing_framework_b200.standin import make_pipeline, tiny_config
+    steps = 6
+    pipe = make_pipeline(tiny_config(), seed=6, device=cuda)
+    pipe.scheduler.set_timesteps(steps)
+    x0 = scenarios.latent(51, (1, 4, 8, 8), cuda)
+    prompt = scenarios.PIPELINE_PROMPTS[:1]
+    inv = nti.NTI()
+    before = _cabi.launch_count()
+    trajectory, context = inv.ddim_inversion_loop(pipe, x0, prompt)
+    found = inv.null_optimization(pipe, trajectory, context, 10, 1e-7, 7.5)
+    assert _cabi.launch_count() - before >= 2 * steps
+    assert len(found) == steps and all(e.shape == (1, 77, 32) and torch.isfinite(e).all() for e in found)
+
+    def reconstruct(**kw):
+        editor = p2p.P2P_NTI(pipe, steps)
+        editor.init_latent = lambda latent, model, h, w, gen, bs: (latent, latent.expand(bs, 4, 8, 8))
+        editor.latent2image = lambda vae, latents: latents          # compare in latent space
+        return editor.text2image_ldm_stable(pipe, prompt, None, num_inference_steps=steps, guidance_scale=7.5, latent=trajectory[-1], **kw)[0]
+
+    err_null = (reconstruct(uncond_embeddings_list=found) - x0).pow(2).mean().item()
+    err_plain = (reconstruct() - x0).pow(2).mean().item()
+    assert err_null < err_plain, (err_null, err_plain)
