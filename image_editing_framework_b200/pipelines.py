@@ -73,7 +73,7 @@ def decode_latents(vae, latents: torch.Tensor, return_type: str = "np"):
     image = (image / 2 + 0.5).clamp(0, 1)
     if return_type == "pt":
         return image
-    return (image.cpu().permute(0, 2, 3, 1).numpy() * 255).astype(np.uint8)
+    return (image.float().cpu().permute(0, 2, 3, 1).numpy() * 255).astype(np.uint8)     # .float(): numpy has no bf16
 
 
 def start_latent(model, latent: Optional[torch.Tensor], height: int, width: int, generator, batch_size: int):
