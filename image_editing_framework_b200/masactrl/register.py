@@ -30,7 +30,8 @@ def regiter_attention_editor_diffusers(model, editor: AttentionBase):
         count = 0
         for _, subnet in net.named_children():
             if net.__class__.__name__ == 'Attention':
-                net._original_forward = net.forward
+                if "_original_forward" not in vars(net):      # a second registration keeps the true original
+                    net._original_forward = net.forward
                 net.forward = _make_forward(net, editor, place_in_unet)
                 return count + 1
             count += visit(subnet, place_in_unet)
@@ -43,13 +44,14 @@ def regiter_attention_editor_diffusers(model, editor: AttentionBase):
                 total += visit(net, place)
                 break
     editor.num_att_layers = total
+    model.unet._ief_installed = editor      # lets the pipeline classes find the editor whose phases key their CUDA graphs
 
 
 def unregister_attention_control(model, editor):
     def restore(net):
         for _, subnet in net.named_children():
-            if hasattr(net, '_original_forward'):
-                net.forward = net._original_forward
+            if '_original_forward' in vars(net):
+                net.forward = vars(net).pop('_original_forward')
             else:
                 restore(subnet)
 
@@ -57,3 +59,4 @@ def unregister_attention_control(model, editor):
         if "down" in name or "mid" in name or "up" in name:
             restore(net)
     editor.num_att_layers = 0
+    model.unet._ief_installed = None

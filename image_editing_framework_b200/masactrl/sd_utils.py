@@ -18,9 +18,12 @@ from .. import pipelines
 
 
 class MasaCtrl:
-    def __init__(self, pipeline, num_inference_steps) -> None:
+    def __init__(self, pipeline, num_inference_steps, graphs: bool = False) -> None:
+        """graphs=True (an extension, off by default): UNet forwards are replayed from CUDA graphs keyed by the registered editor's
+        phase; keep the instance and the editor (editor.reset() between images) to amortise the captures."""
         self.model = pipeline
         self.model.scheduler.set_timesteps(num_inference_steps)
+        self.graphs = graphs
 
     @torch.no_grad()
     def latent2image(self, latents, return_type="np"):
@@ -59,11 +62,12 @@ class MasaCtrl:
             raise AssertionError(f"The shape of input latent tensor {tuple(latents.shape)} should equal to predefined one {shape}.")
         init_latent = latents.clone()
         model.scheduler.set_timesteps(num_inference_steps)
+        runner = pipelines.graph_runner(self, model, getattr(model.unet, "_ief_installed", None))
         for i, t in enumerate(model.scheduler.timesteps.tolist()):
             if ref_intermediate_latents is not None:       # the source branch is re-seated on its inversion trajectory every step
                 latents = torch.cat([ref_intermediate_latents[-1 - i], latents.chunk(2)[1]])
             latents = pipelines.guided_step(model, latents, self._context_for_step(context, i, null_text), t, guidance_scale, extra,
-                                            always_guide=False)
+                                            always_guide=False, runner=runner)
         return self.latent2image(latents, return_type="np"), init_latent
 
     @torch.no_grad()

@@ -55,7 +55,8 @@ def _make_forward(module, controller, place_in_unet):
 
 def _walk(net, place_in_unet, controller) -> int:
     if net.__class__.__name__ == 'Attention':
-        net._original_forward = net.forward
+        if "_original_forward" not in vars(net):      # registering again (every call of the pipeline classes does) keeps the true original
+            net._original_forward = net.forward
         net.forward = _make_forward(net, controller, place_in_unet)
         return 1
     return sum(_walk(child, place_in_unet, controller) for child in net.children()) if hasattr(net, 'children') else 0
@@ -73,12 +74,13 @@ def register_attention_control(model, controller):
     if controller is None:
         controller = DummyController()
     controller.num_att_layers = sum(_walk(child, place, controller) for place, child in _places(model))
+    model.unet._ief_installed = controller
 
 
 def unregister_attention_control(model, controller):
     def restore(net):
-        if hasattr(net, '_original_forward'):
-            net.forward = net._original_forward
+        if '_original_forward' in vars(net):
+            net.forward = vars(net).pop('_original_forward')
         elif hasattr(net, 'children'):
             for child in net.children():
                 restore(child)
@@ -86,3 +88,4 @@ def unregister_attention_control(model, controller):
     for _, child in _places(model):
         restore(child)
     controller.num_att_layers = 0
+    model.unet._ief_installed = None

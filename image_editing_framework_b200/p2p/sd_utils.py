@@ -25,8 +25,11 @@ from .register import register_attention_control
 class P2P:
     height = width = 512
 
-    def __init__(self, model, num_inference_steps) -> None:
+    def __init__(self, model, num_inference_steps, graphs: bool = False) -> None:
+        """graphs=True (an extension, off by default): UNet forwards are replayed from CUDA graphs keyed by the controller's phase;
+        keep the instance and the controller (controller.reset() between images) to amortise the captures."""
         model.scheduler.set_timesteps(num_inference_steps)
+        self.graphs = graphs
 
     # ---- pieces the variants override ---------------------------------------------------------------------------------
     def _conditioning(self, model, prompt: List[str], guidance_scale: float, uncond_embeddings_list):
@@ -59,10 +62,11 @@ class P2P:
         return self.latent2image(model.vae, latents), latent
 
     def _step(self, model, controller, latents, context, t, guidance_scale, extra, low_resource):
+        runner = pipelines.graph_runner(self, model, controller)
         if low_resource:
             raise NotImplementedError("low_resource=True: the reference's two-pass branch passes context[0] / context[1] (2-D rows of the "
                                       "concatenated context) to the UNet and fails inside its attention closure; nothing to reproduce")
-        latents = pipelines.guided_step(model, latents, context, t, guidance_scale, extra)
+        latents = pipelines.guided_step(model, latents, context, t, guidance_scale, extra, runner=runner)
         return controller.step_callback(latents) if controller is not None else latents
 
     def diffusion_step(self, model, controller, latents, context, t, guidance_scale, low_resource=False):

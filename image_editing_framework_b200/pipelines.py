@@ -12,7 +12,9 @@ from typing import Dict, List, Optional, Tuple
 import numpy as np
 import torch
 
+from . import _cabi
 from .ddim import FusedDDIM
+from .graphs import GraphedUNet
 
 
 def text_context(model, prompts: List[str], negative: str = "", with_uncond: bool = True, truncation: bool = True):
@@ -52,18 +54,40 @@ def fused_scheduler(model) -> FusedDDIM:
     return fused
 
 
+def graph_runner(owner, model, controller, key_fn=None) -> Optional[GraphedUNet]:
+    """The CUDA-graph runner of a pipeline-class instance built with graphs=True (None otherwise). It lives as long as the instance and
+    is rebuilt when the UNet or the installed controller / editor changes: captured kernels read that controller's device tables, and
+    its graph_key() names the phase a step replays (graphs.GraphedUNet). Reuse pays when one instance + one controller (reset()
+    between images) serve many edits; a one-off call roughly breaks even (each phase is captured on its second occurrence)."""
+    if not getattr(owner, "graphs", False):
+        return None
+    runner = getattr(owner, "_runner", None)
+    if runner is None or runner.unet is not model.unet or runner.controller is not controller:
+        if runner is not None:
+            runner.close()
+        runner = owner._runner = GraphedUNet(model.unet, controller, key_fn, launch_counter=_cabi.launch_count)
+    runner.key_fn = key_fn
+    return runner
+
+
+def unet_eps(model, x: torch.Tensor, t, context: torch.Tensor, unet_kwargs: Optional[dict] = None,
+             runner: Optional[GraphedUNet] = None) -> torch.Tensor:
+    """One noise prediction; replayed from the runner's graph when there is one and no extra UNet argument is in play."""
+    kw = unet_kwargs or {}
+    if runner is not None and all(v is None for v in kw.values()):
+        return runner(x, t, context)
+    return model.unet(x, t, encoder_hidden_states=context, **kw)["sample"]
+
+
 def guided_step(model, latents: torch.Tensor, context: torch.Tensor, t, guidance_scale: float, unet_kwargs: Optional[dict] = None,
-                always_guide: bool = True) -> torch.Tensor:
+                always_guide: bool = True, runner: Optional[GraphedUNet] = None) -> torch.Tensor:
     """unet(cat[latents]*2) -> uncond + g (cond - uncond) -> DDIM step, the last two in one kernel launch.
     `always_guide=False` follows the drivers that skip guidance when guidance_scale <= 1 (single forward, plain step)."""
     fused = fused_scheduler(model)
     t = int(t)
-    kw = unet_kwargs or {}
     if always_guide or guidance_scale > 1.0:
-        eps = model.unet(torch.cat([latents] * 2), t, encoder_hidden_states=context, **kw)["sample"]
-        return fused.step(eps, t, latents, guidance_scale)
-    eps = model.unet(latents, t, encoder_hidden_states=context, **kw)["sample"]
-    return fused.step(eps, t, latents, None)
+        return fused.step(unet_eps(model, torch.cat([latents] * 2), t, context, unet_kwargs, runner), t, latents, guidance_scale)
+    return fused.step(unet_eps(model, latents, t, context, unet_kwargs, runner), t, latents, None)
 
 
 @torch.no_grad()

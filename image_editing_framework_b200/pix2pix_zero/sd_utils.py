@@ -21,9 +21,11 @@ from .attention_control import prep_unet
 
 
 class P2P_Zero:
-    def __init__(self, pipeline, num_inference_steps):
+    def __init__(self, pipeline, num_inference_steps, graphs: bool = False):
+        """graphs=True (an extension, off by default): the no-grad forwards of both loops are replayed from a CUDA graph."""
         self.model = pipeline
         self.model.scheduler.set_timesteps(num_inference_steps)
+        self.graphs = graphs
 
     # ---- what the variants differ in -----------------------------------------------------------------------------------
     def _conditioning(self, text, device, guided, num_images_per_prompt, negative_prompt, prompt_embeds, negative_prompt_embeds,
@@ -63,7 +65,8 @@ class P2P_Zero:
             latents = model.prepare_latents(num_images_per_prompt, model.unet.config.in_channels, height, width, src.dtype, device,
                                             generator, latents)
         rec, edited = editing.pix2pix_zero_edit(model, src, edit, latents, num_inference_steps, guidance_scale, guidance_amount,
-                                                only_sample=only_sample, uncond_embeddings_list=uncond_embeddings_list,
+                                                only_sample=only_sample, graphs=self.graphs and not kw_src and not kw_edit,
+                                                uncond_embeddings_list=uncond_embeddings_list,
                                                 unet_kwargs_src=kw_src, unet_kwargs_edit=kw_edit)
         image_rec = self.latent2image(rec)
         return image_rec if only_sample else (image_rec, self.latent2image(edited))

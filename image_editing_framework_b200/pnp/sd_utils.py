@@ -27,9 +27,12 @@ class PnP:
     _unregister_attn = staticmethod(hooks.unregister_attention_control_efficient)
     _unregister_conv = staticmethod(hooks.unregister_conv_control_efficient)
 
-    def __init__(self, pipeline, num_inference_steps) -> None:
+    def __init__(self, pipeline, num_inference_steps, graphs: bool = False) -> None:
+        """graphs=True (an extension, off by default): UNet forwards are replayed from CUDA graphs keyed by which injections the
+        timestep switches on; keep the instance to amortise the captures over edits."""
         self.model = pipeline
         self.model.scheduler.set_timesteps(num_inference_steps)
+        self.graphs = graphs
 
     def init_pnp(self, conv_injection_t, qk_injection_t):
         ts = self.model.scheduler.timesteps
@@ -69,6 +72,9 @@ class PnP:
         latents = model.prepare_latents(num_images_per_prompt, channels, height, width, context.dtype, device, generator, latents)
         latents = latents.expand(batch_size, channels, height // 8, width // 8)
         self.init_pnp(conv_injection_t=int(num_inference_steps * pnp_f_t), qk_injection_t=int(num_inference_steps * pnp_attn_t))
+        qk_on = frozenset(int(t) for t in self.qk_injection_timesteps)
+        conv_on = frozenset(int(t) for t in self.conv_injection_timesteps)
+        runner = pipelines.graph_runner(self, model, None, lambda t: (t in qk_on or t == 1000, t in conv_on or t == 1000))
         try:
             for i, t in enumerate(model.scheduler.timesteps.tolist()):
                 self._register_time(model, t)
@@ -76,7 +82,8 @@ class PnP:
                     half = context.shape[0] // 2
                     context[:half] = uncond_embeddings_list[i].expand(*context[half:].shape)
                 latents = pipelines.guided_step(model, latents, context, t, guidance_scale,
-                                                dict(extra, cross_attention_kwargs=cross_attention_kwargs), always_guide=False)
+                                                dict(extra, cross_attention_kwargs=cross_attention_kwargs), always_guide=False,
+                                                runner=runner)
             return self.latent2image(latents)
         finally:
             self._unregister_attn(model)

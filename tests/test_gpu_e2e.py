@@ -341,3 +341,53 @@ def test_null_text_inversion_runs_on_the_fused_step(cuda):
     err_null = (reconstruct(uncond_embeddings_list=found) - x0).pow(2).mean().item()
     err_plain = (reconstruct() - x0).pow(2).mean().item()
     assert err_null < err_plain, (err_null, err_plain)
+
+
+@pytest.mark.parametrize("family", ["p2p", "masactrl", "pnp", "pix2pix-zero"])
+def test_pipeline_classes_graph_replay_matches_eager(cuda, family):
+    """graphs=True on the reference-named classes: same images as the eager call (to one uint8 step), forwards actually replayed, and
+    a second edit on the same instance + controller reuses the captured graphs."""
+    from image_editing_framework_b200.standin import make_pipeline, tiny_config
+    import image_editing_framework_b200 as pkg
+    steps = 6
+    pipe = make_pipeline(tiny_config(), seed=3, device=cuda)
+    lat = scenarios.latent(8, (1, 4, 8, 8), cuda)
+    prompts = scenarios.PIPELINE_PROMPTS
+
+    def edit(graphs, state={}):
+        key = (family, graphs)
+        if family == "p2p":
+            ctrl, editor = state.get(key) or (pkg.p2p.AttentionReplace(prompts, pipe.tokenizer, steps, 0.8, 0.5, device=cuda), pkg.p2p.P2P(pipe, steps, graphs=graphs))
+            state[key] = (ctrl, editor)
+            ctrl.reset()
+            editor.init_latent = lambda latent, model, h, w, gen, bs: (latent, latent.expand(bs, 4, 8, 8))
+            try:
+                return editor.text2image_ldm_stable(pipe, prompts, ctrl, num_inference_steps=steps, latent=lat)[0], editor
+            finally:
+                pkg.p2p.unregister_attention_control(pipe, ctrl)
+        if family == "masactrl":
+            ed, editor = state.get(key) or (pkg.masactrl.MutualSelfAttentionControl(2, 10, total_steps=steps), pkg.masactrl.MasaCtrl(pipe, steps, graphs=graphs))
+            state[key] = (ed, editor)
+            ed.reset()
+            pkg.masactrl.regiter_attention_editor_diffusers(pipe, ed)
+            try:
+                return editor(prompts, height=64, width=64, num_inference_steps=steps, latents=torch.cat([lat, lat]))[0], editor
+            finally:
+                pkg.masactrl.unregister_attention_control(pipe, ed)
+        if family == "pnp":
+            editor = state.setdefault(key, pkg.pnp.PnP(pipe, steps, graphs=graphs))
+            return editor(prompts, height=64, width=64, num_inference_steps=steps, latents=lat, pnp_attn_t=0.5, pnp_f_t=0.8), editor
+        editor = state.setdefault(key, pkg.pix2pix_zero.P2P_Zero(pipe, steps, graphs=graphs))
+        try:
+            return editor(prompts, height=64, width=64, num_inference_steps=steps, latents=lat.clone())[1], editor
+        finally:
+            pkg.pix2pix_zero.restore_original_processors(pipe.unet, editor.original_processors)
+
+    want, _ = edit(False)
+    first, editor = edit(True)
+    second, editor = edit(True)
+    for got in (first, second):
+        assert abs(got.astype("int16") - want.astype("int16")).max() <= 1
+    if family != "pix2pix-zero":        # (that driver builds its runner per call)
+        runner = editor._runner
+        assert runner.replays > steps and runner.captures <= 4, (runner.replays, runner.captures, runner.eager_calls)
