@@ -53,7 +53,12 @@ class FusedDDIM:
 
 
 class ddim_inversion:
-    """Same method names as the reference class (*/inversion/ddim.py:7-58); only the arithmetic moved to the kernel."""
+    """Same method names as the reference class (*/inversion/ddim.py:7-58); only the arithmetic moved to the kernel.
+
+    `graphs` (an extension, off by default; set it on the class or an instance): the inversion's UNet forwards are replayed from a
+    CUDA graph kept on the UNet. Only while no attention controller is registered — a replay would skip its counters."""
+
+    graphs = False
 
     def ddim_reverse(self, model, model_output, timestep, sample):
         fused = getattr(model, "_ief_fused_ddim", None)
@@ -73,8 +78,16 @@ class ddim_inversion:
         """The loop both classes share: the scheduler's timesteps walked backwards, one UNet forward + one fused reverse step each."""
         trajectory = [latent]
         latent = latent.clone().detach()
+        runner = None
+        extras = [v for k, v in unet_kwargs.items() if k != "encoder_hidden_states"]
+        if self.graphs and latent.is_cuda and all(v is None for v in extras) and getattr(model.unet, "_ief_installed", None) is None:
+            from .graphs import GraphedUNet
+            runner = getattr(model.unet, "_ief_plain_runner", None)
+            if runner is None or runner.unet is not model.unet:
+                runner = model.unet._ief_plain_runner = GraphedUNet(model.unet)
         for t in reversed(model.scheduler.timesteps.tolist()):   # one host copy instead of a device sync per step
-            noise_pred = model.unet(latent, t, **unet_kwargs).sample
+            noise_pred = runner(latent, t, unet_kwargs["encoder_hidden_states"]) if runner is not None else \
+                model.unet(latent, t, **unet_kwargs).sample
             latent = self.ddim_reverse(model, noise_pred, t, latent)
             trajectory.append(latent)
         return trajectory

@@ -394,3 +394,18 @@ def test_pipeline_classes_graph_replay_matches_eager(cuda, family):
     if family != "pix2pix-zero":        # (that driver builds its runner per call)
         runner = editor._runner
         assert runner.replays > steps and runner.captures <= 4, (runner.replays, runner.captures, runner.eager_calls)
+
+
+def test_ddim_inversion_graph_replay_matches_eager(cuda):
+    from image_editing_framework_b200.ddim import ddim_inversion
+    from image_editing_framework_b200.standin import make_pipeline, tiny_config
+    pipe = make_pipeline(tiny_config(), seed=4, device=cuda)
+    pipe.scheduler.set_timesteps(8)
+    x0 = scenarios.latent(9, (1, 4, 8, 8), cuda)
+    want, _ = ddim_inversion().ddim_inversion_loop(pipe, x0, scenarios.PIPELINE_PROMPTS[:1])
+    inv = ddim_inversion()
+    inv.graphs = True
+    got, _ = inv.ddim_inversion_loop(pipe, x0, scenarios.PIPELINE_PROMPTS[:1])
+    runner = pipe.unet._ief_plain_runner
+    assert runner.replays >= 6 and runner.captures == 1
+    assert len(got) == len(want) == 9 and all(torch.allclose(a, b, atol=1e-4, rtol=1e-4) for a, b in zip(got, want))
