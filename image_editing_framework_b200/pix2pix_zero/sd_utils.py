@@ -22,7 +22,9 @@ from .attention_control import prep_unet
 
 class P2P_Zero:
     def __init__(self, pipeline, num_inference_steps, graphs: bool = False):
-        """graphs=True (an extension, off by default): the no-grad forwards of both loops are replayed from a CUDA graph."""
+        """graphs=True (an extension, off by default): the no-grad forwards of both loops are replayed from a CUDA graph. The graph is
+        rebuilt per call (the guidance pass re-points the modules' attn_probs, so a captured map buffer cannot outlive an edit); at 50
+        steps the capture costs about what the replays save."""
         self.model = pipeline
         self.model.scheduler.set_timesteps(num_inference_steps)
         self.graphs = graphs
