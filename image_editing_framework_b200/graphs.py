@@ -86,42 +86,50 @@ class GraphedUNet:
             self.controller._graph_mode = False
         self._graphs.clear()
 
-    def __call__(self, x: torch.Tensor, t, ctx: torch.Tensor) -> torch.Tensor:
+    def __call__(self, x: torch.Tensor, t, ctx: torch.Tensor, added_cond_kwargs: Optional[Dict[str, torch.Tensor]] = None) -> torch.Tensor:
+        """`added_cond_kwargs` (SDXL's pooled text embedding + size ids) are tensor inputs like x and ctx: copied into static buffers."""
         c = self.controller
+        extra = {"added_cond_kwargs": added_cond_kwargs} if added_cond_kwargs is not None else {}
         ckey = c.graph_key() if c is not None else ()
         if c is not None:
             c.graph_prepare()
         t_host = int(t) if not torch.is_tensor(t) else None
         if ckey is None:
             self.eager_calls += 1
-            return self.unet(x, t, encoder_hidden_states=ctx)["sample"]
-        key = (tuple(x.shape), x.dtype, tuple(ctx.shape), ckey, self.key_fn(t_host) if self.key_fn is not None else ())
+            return self.unet(x, t, encoder_hidden_states=ctx, **extra)["sample"]
+        added_sig = tuple(sorted((k, tuple(v.shape), v.dtype) for k, v in added_cond_kwargs.items())) if added_cond_kwargs is not None else None
+        key = (tuple(x.shape), x.dtype, tuple(ctx.shape), ckey, self.key_fn(t_host) if self.key_fn is not None else (), added_sig)
         n = self._seen.get(key, 0)
         self._seen[key] = n + 1
         td = self._tstep(t, x.device)
         if n == 0:
             self.eager_calls += 1
-            return self.unet(x, td, encoder_hidden_states=ctx)["sample"]
+            return self.unet(x, td, encoder_hidden_states=ctx, **extra)["sample"]
         if n == 1:
             xs, ts, cs = x.clone(), td.clone(), ctx.clone()
+            added_s = {k: v.clone() for k, v in added_cond_kwargs.items()} if added_cond_kwargs is not None else None
+            extra_s = {"added_cond_kwargs": added_s} if added_s is not None else {}
             graph = torch.cuda.CUDAGraph()
             if self._pool is None:
                 self._pool = torch.cuda.graph_pool_handle()
             before = self.launch_counter() if self.launch_counter else 0
             with torch.cuda.graph(graph, pool=self._pool), torch.no_grad():
-                out = self.unet(xs, ts, encoder_hidden_states=cs)["sample"]
+                out = self.unet(xs, ts, encoder_hidden_states=cs, **extra_s)["sample"]
             launches = (self.launch_counter() - before) if self.launch_counter else 0
-            self._graphs[key] = (graph, xs, ts, cs, out, launches)
+            self._graphs[key] = (graph, xs, ts, cs, out, launches, added_s)
             self.captures += 1
             graph.replay()
             self.replays += 1
             self.replayed_launches += launches
             return out
-        graph, xs, ts, cs, out, launches = self._graphs[key]
+        graph, xs, ts, cs, out, launches, added_s = self._graphs[key]
         xs.copy_(x, non_blocking=True)
         ts.copy_(td, non_blocking=True)
         if cs.data_ptr() != ctx.data_ptr():
             cs.copy_(ctx, non_blocking=True)
+        if added_s is not None:
+            for k, buf in added_s.items():
+                buf.copy_(added_cond_kwargs[k], non_blocking=True)
         graph.replay()
         self.replays += 1
         self.replayed_launches += launches

@@ -72,10 +72,11 @@ def graph_runner(owner, model, controller, key_fn=None) -> Optional[GraphedUNet]
 
 def unet_eps(model, x: torch.Tensor, t, context: torch.Tensor, unet_kwargs: Optional[dict] = None,
              runner: Optional[GraphedUNet] = None) -> torch.Tensor:
-    """One noise prediction; replayed from the runner's graph when there is one and no extra UNet argument is in play."""
+    """One noise prediction; replayed from the runner's graph when there is one and the only extra UNet argument in play is SDXL's
+    added_cond_kwargs (tensor inputs the runner copies like x and the context)."""
     kw = unet_kwargs or {}
-    if runner is not None and all(v is None for v in kw.values()):
-        return runner(x, t, context)
+    if runner is not None and all(v is None for k, v in kw.items() if k != "added_cond_kwargs"):
+        return runner(x, t, context, kw.get("added_cond_kwargs"))
     return model.unet(x, t, encoder_hidden_states=context, **kw)["sample"]
 
 

@@ -409,3 +409,28 @@ def test_ddim_inversion_graph_replay_matches_eager(cuda):
     runner = pipe.unet._ief_plain_runner
     assert runner.replays >= 6 and runner.captures == 1
     assert len(got) == len(want) == 9 and all(torch.allclose(a, b, atol=1e-4, rtol=1e-4) for a, b in zip(got, want))
+
+
+def test_xl_pipeline_class_graph_replay_carries_added_cond_kwargs(cuda):
+    """graphs=True on an SDXL class: the pooled embedding / size ids travel as copied graph inputs, results match the eager call."""
+    import image_editing_framework_b200 as pkg
+    from image_editing_framework_b200.standin import tiny_config
+    steps = 6
+    pipe = scenarios.XLPipelineDouble(5, tiny_config(), cuda)
+    lat = scenarios.latent(10, (1, 4, 8, 8), cuda)
+    ed = pkg.masactrl.MutualSelfAttentionControl(2, 10, total_steps=steps)
+
+    def edit(editor):
+        ed.reset()
+        pkg.masactrl.regiter_attention_editor_diffusers(pipe, ed)
+        try:
+            return editor(scenarios.PIPELINE_PROMPTS, height=64, width=64, num_inference_steps=steps, latents=torch.cat([lat, lat]))[0]
+        finally:
+            pkg.masactrl.unregister_attention_control(pipe, ed)
+
+    want = edit(pkg.masactrl.MasaCtrl_XL(pipe, steps))
+    graphed = pkg.masactrl.MasaCtrl_XL(pipe, steps, graphs=True)
+    for _ in range(2):
+        got = edit(graphed)
+        assert abs(got.astype("int16") - want.astype("int16")).max() <= 1
+    assert graphed._runner.replays > steps
