@@ -325,7 +325,7 @@ def run_ours(args):
     }
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_sample(args)
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -402,10 +402,32 @@ def run_reference(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"configs[1]: MasaCtrl mutual self-attention, SD-1.5 512^2, {args.ddim_steps}+{args.ddim_steps} UNet forwards; bounded CPU sample per step"},
             "cpu_baseline": base, "e2e": {"value": v, "unit": "edits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout, but libraries write to file descriptor 1 behind Python's back (NCCL prints its version
+    banner there under torchrun). Keep a private copy of the real stdout for the result line and point fd 1 at stderr for everyone else."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    payload = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(payload.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, payload)
 
 
 if __name__ == "__main__":
+    claim_stdout()
     a = parse()
     if a.impl == "reference":
         run_reference(a)
