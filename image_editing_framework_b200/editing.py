@@ -119,8 +119,8 @@ def _cross_modules(unet):
 
 
 def pix2pix_zero_edit(model, embeds_src: torch.Tensor, embeds_edit: torch.Tensor, latents: torch.Tensor, num_inference_steps: int = 50,
-                      guidance_scale: float = 7.5, guidance_amount: float = 0.1, only_sample: bool = False, graphs: bool = False,
-                      map_dtype: torch.dtype = torch.float32, uncond_embeddings_list=None, unet_kwargs_src: Optional[dict] = None,
+                      guidance_scale: float = 7.5, guidance_amount: float = 0.1, only_sample: bool = False,
+                      graphs: Union[bool, GraphedUNet] = False, map_dtype: torch.dtype = torch.float32, uncond_embeddings_list=None, unet_kwargs_src: Optional[dict] = None,
                       unet_kwargs_edit: Optional[dict] = None):
     """Pix2Pix-zero's two denoising loops on latents (pix2pix-zero/model/sd_utils.py:86-182). The UNet must carry MyAttnProcessor
     (prep_unet). embeds_*: [uncond, cond] context pairs ([2, 77, C]); latents: [1, 4, h, w]. Returns (reconstruction latents,
@@ -141,20 +141,30 @@ def pix2pix_zero_edit(model, embeds_src: torch.Tensor, embeds_edit: torch.Tensor
     ts = model.scheduler.timesteps.tolist()
     cross = _cross_modules(model.unet)
     latents_init = latents.clone()
-    runner = GraphedUNet(model.unet, None, None, launch_counter=_cabi.launch_count) if graphs else None
+    # graphs=True: a runner for this call only; a GraphedUNet built once for this unet (controller None) amortises the captures over edits
+    own = graphs is True
+    runner = GraphedUNet(model.unet, None, None, launch_counter=_cabi.launch_count) if own else (graphs or None)
     ref_maps = {}
     with torch.no_grad():  # loop 1: reference maps (:92-122)
         for i, t in enumerate(ts):
             if uncond_embeddings_list is not None:
                 embeds_src[0] = uncond_embeddings_list[i]
             x = torch.cat([latents] * 2)
+            replays = runner.replays if runner is not None else 0
             eps = runner(x, t, embeds_src) if runner is not None else model.unet(x, t, encoder_hidden_states=embeds_src, **kw_src)["sample"]
-            # a replayed graph rewrites the same attn_probs buffers every step: the cache must own its copy either way
-            ref_maps[t] = [m.attn_probs.detach().to(map_dtype, copy=True) for _, m in cross]
+            maps = [m.attn_probs for _, m in cross]
+            if runner is not None and runner.replays > replays:
+                # a replay writes the buffers the capture allocated, whatever the modules' attn_probs point to by now (the guidance
+                # pass of an earlier edit re-pointed them): remember them when the capture happens, read them afterwards
+                if getattr(runner, "_map_buffers", None) is None:
+                    runner._map_buffers = maps
+                maps = runner._map_buffers
+            # those buffers are rewritten every step: the cache must own its copy either way
+            ref_maps[t] = [p.detach().to(map_dtype, copy=True) for p in maps]
             latents = fused.step(eps, t, latents, guidance_scale)
     latents_rec = latents
     if only_sample:
-        if runner is not None:
+        if own:
             runner.close()
         return latents_rec, None
     latents = latents_init
@@ -174,6 +184,6 @@ def pix2pix_zero_edit(model, embeds_src: torch.Tensor, embeds_edit: torch.Tensor
                 model.unet(x_new, t, encoder_hidden_states=embeds_edit, **kw_edit)["sample"]
             latents = x_new.chunk(2)[0]
             latents = fused.step(eps, t, latents, guidance_scale)
-    if runner is not None:
+    if own:
         runner.close()
     return latents_rec, latents

@@ -22,9 +22,8 @@ from .attention_control import prep_unet
 
 class P2P_Zero:
     def __init__(self, pipeline, num_inference_steps, graphs: bool = False):
-        """graphs=True (an extension, off by default): the no-grad forwards of both loops are replayed from a CUDA graph. The graph is
-        rebuilt per call (the guidance pass re-points the modules' attn_probs, so a captured map buffer cannot outlive an edit); at 50
-        steps the capture costs about what the replays save."""
+        """graphs=True (an extension, off by default): the no-grad forwards of both loops are replayed from a CUDA graph kept on this
+        instance, so keep the instance to amortise the capture over edits."""
         self.model = pipeline
         self.model.scheduler.set_timesteps(num_inference_steps)
         self.graphs = graphs
@@ -67,7 +66,8 @@ class P2P_Zero:
             latents = model.prepare_latents(num_images_per_prompt, model.unet.config.in_channels, height, width, src.dtype, device,
                                             generator, latents)
         rec, edited = editing.pix2pix_zero_edit(model, src, edit, latents, num_inference_steps, guidance_scale, guidance_amount,
-                                                only_sample=only_sample, graphs=self.graphs and not kw_src and not kw_edit,
+                                                only_sample=only_sample,
+                                                graphs=(pipelines.graph_runner(self, model, None) if not (kw_src or kw_edit) else None) or False,
                                                 uncond_embeddings_list=uncond_embeddings_list,
                                                 unet_kwargs_src=kw_src, unet_kwargs_edit=kw_edit)
         image_rec = self.latent2image(rec)

@@ -391,9 +391,8 @@ def test_pipeline_classes_graph_replay_matches_eager(cuda, family):
             assert psnr(torch.from_numpy(got).float(), torch.from_numpy(want).float()) >= PSNR_DB
         else:
             assert abs(got.astype("int16") - want.astype("int16")).max() <= 1
-    if family != "pix2pix-zero":        # (that driver builds its runner per call)
-        runner = editor._runner
-        assert runner.replays > steps and runner.captures <= 4, (runner.replays, runner.captures, runner.eager_calls)
+    runner = editor._runner
+    assert runner.replays > steps and runner.captures <= 4, (runner.replays, runner.captures, runner.eager_calls)
 
 
 def test_ddim_inversion_graph_replay_matches_eager(cuda):
