@@ -73,21 +73,21 @@ def main():
     out = {}
     GRAPHS = [False]
     for graphs in (False, True):
-      GRAPHS[0] = graphs
-      for name, fn in (("P2P (AttentionReplace)", case_p2p), ("MasaCtrl (+ DDIM inversion)", case_masactrl), ("PnP", case_pnp),
-                     ("P2P_Zero (sample + guided edit)", case_p2z)):
-        with contextlib.redirect_stdout(io.StringIO()):
-            for _ in range(2 if graphs else 1):    # warm-up (cuDNN autotune, allocator; with graphs: first eager pass + captures)
-                fn()
-            torch.cuda.synchronize()
-            l0, t0 = _cabi.launch_count(), time.perf_counter()
-            image = fn()
-            torch.cuda.synchronize()
-            dt = time.perf_counter() - t0
-        assert image.dtype.name == "uint8" and image.shape[1:] == (512, 512, 3), (image.dtype, image.shape)
-        name = name + (" graphs=True" if graphs else "")
-        out[name] = {"s_per_call": round(dt, 3), "calls_per_s": round(1 / dt, 3), "ief_launches_outside_graphs": _cabi.launch_count() - l0}
-        print(name, out[name], flush=True)
+        GRAPHS[0] = graphs
+        for name, fn in (("P2P (AttentionReplace)", case_p2p), ("MasaCtrl (+ DDIM inversion)", case_masactrl), ("PnP", case_pnp),
+                         ("P2P_Zero (sample + guided edit)", case_p2z)):
+            with contextlib.redirect_stdout(io.StringIO()):
+                for _ in range(2 if graphs else 1):    # warm-up (cuDNN autotune, allocator; with graphs: first eager pass + captures)
+                    fn()
+                torch.cuda.synchronize()
+                l0, t0 = _cabi.launch_count(), time.perf_counter()
+                image = fn()
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+            assert image.dtype.name == "uint8" and image.shape[1:] == (512, 512, 3), (image.dtype, image.shape)
+            name = name + (" graphs=True" if graphs else "")
+            out[name] = {"s_per_call": round(dt, 3), "calls_per_s": round(1 / dt, 3), "ief_launches_outside_graphs": _cabi.launch_count() - l0}
+            print(name, out[name], flush=True)
     print(json.dumps({"model": "sd15 stand-in, bf16, channels_last", "ddim_steps": STEPS, "results": out}))
 
 
