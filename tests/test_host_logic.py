@@ -528,3 +528,30 @@ def test_pipeline_classes_reproduce_reference_images(monkeypatch, family, name):
     assert len(got) == len(want)
     for a, b in zip(got, want):
         assert a.dtype == np.uint8 and np.abs(a.astype(np.int16) - b.numpy().astype(np.int16)).max() <= 1
+
+
+def test_reference_script_flow_after_import_switch(monkeypatch):
+    """The masactrl/edit_real.py flow INTEGRATION.md shows (image -> latent -> DDIM inversion -> register editor -> MasaCtrl sampler),
+    and its null-text variant, run unchanged on this package's names."""
+    cpu_backend.install(monkeypatch)
+    from image_editing_framework_b200.ddim import ddim_inversion
+    from image_editing_framework_b200.nti import NTI
+    from image_editing_framework_b200.masactrl import (MasaCtrl, MasaCtrl_NTI, MutualSelfAttentionControl, regiter_attention_editor_diffusers,
+                                                       unregister_attention_control)
+    pipe = make_pipeline(tiny_config(), seed=0)
+    steps = 3
+    image = np.random.default_rng(0).integers(0, 256, (64, 64, 3), dtype=np.uint8)
+    source_prompt, target_prompt = ["a cat"], ["a dog"]
+    for invertor, editor in ((ddim_inversion(), MasaCtrl(pipe, steps)), (NTI(), MasaCtrl_NTI(pipe, steps))):
+        latent = invertor.image2latent(model=pipe, image=image, device="cpu", dtype=torch.float32)
+        latents, context = invertor.ddim_inversion_loop(pipe, latent, source_prompt)
+        extra = {}
+        if isinstance(invertor, NTI):
+            extra["uncond_embeddings_list"] = invertor.null_optimization(pipe, latents, context, 2, 1e-5, 7.5)
+        controller = MutualSelfAttentionControl(1, 10, total_steps=steps, model_type="SD")
+        regiter_attention_editor_diffusers(editor.model, controller)
+        images, x_t = editor(prompt=source_prompt + target_prompt, latents=torch.cat([latents[-1]] * 2), guidance_scale=7.5,
+                             num_inference_steps=steps, height=64, width=64, **extra)
+        unregister_attention_control(pipe, controller)
+        assert images.shape == (2, 64, 64, 3) and images.dtype == np.uint8 and controller.cur_step == steps
+        assert not np.array_equal(images[0], images[1])       # two prompts, two images
