@@ -19,7 +19,8 @@ IEF_IMPL_AUTO, IEF_IMPL_MMA, IEF_IMPL_TCGEN05 = 0, 1, 2
 IEF_EDIT_NONE, IEF_EDIT_REPLACE, IEF_EDIT_REFINE = 0, 1, 2
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "libief_b200.so")
+# IEF_LIB_PATH: an alternative build of the same library (A/B kernel variants from tools/build_variants.sh); never a different backend
+LIB_PATH = os.environ.get("IEF_LIB_PATH") or os.path.join(_PKG_DIR, "libief_b200.so")
 BUILD_SCRIPT = os.path.join(_PKG_DIR, "csrc", "build.sh")
 
 

@@ -7,7 +7,9 @@ namespace {
 thread_local char g_err[512] = "";
 thread_local const char* g_last_impl = "none";
 std::atomic<int64_t> g_launches{0};
-long long* g_trace = nullptr;
+#if defined(IEF_TC3_TRACE) && IEF_TC3_TRACE
+long long* g_trace = nullptr;  // debug builds only (IEF_EXTRA_NVCC_FLAGS=-DIEF_TC3_TRACE=1): the shipped library keeps no mutable global state
+#endif
 }  // namespace
 
 void ief_set_error(const char* fmt, ...) {
@@ -16,9 +18,13 @@ void ief_set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+#if defined(IEF_TC3_TRACE) && IEF_TC3_TRACE
 long long* ief_debug_trace_buffer() { return g_trace; }
-// Debug only (not part of the ABI header): device buffer of >= 1536 int64 receiving clock64 phase stamps of CTA (0,0,0).
+// Debug builds only (not part of the ABI header): device buffer of >= 1600 int64 receiving clock64 phase stamps of CTA 0.
 extern "C" void ief_debug_set_trace_buffer(long long* p) { g_trace = p; }
+#else
+long long* ief_debug_trace_buffer() { return nullptr; }
+#endif
 void ief_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 extern "C" int ief_abi_version(void) { return IEF_ABI_VERSION; }

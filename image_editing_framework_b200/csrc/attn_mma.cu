@@ -225,11 +225,7 @@ template <int DTYPE, int DP, bool WRITE_P>
 int launch_one(const MmaArgs& a, dim3 grid, cudaStream_t st) {
   constexpr int smem = (kBM + 4 * kBN) * (DP + 8) * 2;  // Q + two stages of K, V
   auto kern = attn_mma_kernel<DTYPE, DP, WRITE_P>;
-  static bool configured = false;
-  if (!configured) {
-    IEF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
+  IEF_CONFIG_SMEM(kern, smem);
   kern<<<grid, kThreads, smem, st>>>(a);
   IEF_LAUNCH_OK("attn_mma_kernel");
   return IEF_OK;
@@ -344,11 +340,7 @@ template <int DTYPE, int DP>
 int launch_probs_one(const MmaArgs& a, const float* lse, dim3 grid, cudaStream_t st) {
   constexpr int smem = (kBM + 2 * kBN) * (DP + 8) * 2;
   auto kern = attn_probs_from_lse_kernel<DTYPE, DP>;
-  static bool configured = false;
-  if (!configured) {
-    IEF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
+  IEF_CONFIG_SMEM(kern, smem);
   // enough CTAs for ~6 per SM: split the key range when the (row, head, query tile) grid alone is too small
   int stored_rows = 0;
   for (int i = 0; i < a.B; ++i) stored_rows += (a.rows.active[i] && a.rows.pslot[i] >= 0) ? 1 : 0;

@@ -310,11 +310,7 @@ int make_map(CUtensorMap* m, int dtype, const ief_tensor4& t, int d, int N, int 
 template <int DTYPE, int DCH>
 int launch_tc(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const TcArgs& a, dim3 grid, cudaStream_t st) {
   auto kern = attn_tc_kernel<DTYPE, DCH>;
-  static bool configured = false;  // per template instance
-  if (!configured) {
-    IEF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<DCH>::kSmemBytes));
-    configured = true;
-  }
+  IEF_CONFIG_SMEM(kern, TcCfg<DCH>::kSmemBytes);
   kern<<<grid, kThreads, TcCfg<DCH>::kSmemBytes, st>>>(mq, mk, mv, a);
   IEF_LAUNCH_OK("attn_tc_kernel");
   return IEF_OK;
@@ -353,15 +349,13 @@ __global__ void __launch_bounds__(128) key_norm_kernel(const __nv_bfloat16* k, i
   if (threadIdx.x == 0) out[((int64_t)b * H + h) * ntb + tile] = sqrtf(fmaxf(fmaxf(part[0], part[1]), fmaxf(part[2], part[3]))) * 1.001f;
 }
 
-// Where the key-norm pre-pass pays (measured, profiles/r01_kernel_microbench_gen3b.jsonl): head dims 49..64 (no free accumulator
-// columns for the row-sum MMA, so the maximum pass is a larger share of the softmax instructions) and >= 24 key tiles (the
-// pre-pass launch costs 4-5 us): +3..7 %. At head_dim <= 48 and on short sequences it loses 3-13 %.
+// The key-norm pre-pass (guarded skipping of the maximum pass, attn_tc3 MAXMODE 1) gained 3-7 % at head dims 49..64 and lost 3-13 %
+// elsewhere (profiles/r01_kernel_microbench_gen3b.jsonl); the optimistic unshifted loop (MAXMODE 2) supersedes it without a
+// pre-pass. It stays reachable for A/B runs with IEF_TC3_SKIPMAX=2.
 static bool key_norm_prepass_pays(const ief_attn_params* p) {
-  static int force = -1;  // IEF_TC3_SKIPMAX=2: pre-pass wherever the kernel supports it (A/B runs)
+  static int force = -1;
   if (force < 0) { const char* e = getenv("IEF_TC3_SKIPMAX"); force = (e && atoi(e) == 2) ? 1 : 0; }
-  if (force) return p->dtype == IEF_BF16 && p->d <= 64 && p->Nq >= 512 && p->key_bias == nullptr && p->probs_out == nullptr;
-  return p->dtype == IEF_BF16 && p->d > 48 && p->d <= 64 && p->Nq >= 512 && ief_ceil_div(p->Nk, 128) * (p->k_src2 ? 2 : 1) >= 24 &&
-         p->key_bias == nullptr && p->probs_out == nullptr;
+  return force && p->dtype == IEF_BF16 && p->d <= 64 && p->Nq >= 512 && p->key_bias == nullptr && p->probs_out == nullptr;
 }
 
 // Stored maps (probs_out) of layers the tcgen05 kernels serve: O and the row log-sum-exp from them, then one QK^T sweep that writes
@@ -429,6 +423,9 @@ int ief_attn_tc_launch(const ief_attn_params* p, const IefRowTable& rows, cudaSt
   for (int i = 0; i < p->B; ++i)
     if (rows.bias[i] >= 0) a.key_bias = p->key_bias;
   a.sum_mma = (a.dv_mma <= 48 && getenv("IEF_TC3_NO_SUM_MMA") == nullptr) ? 1 : 0;
+  static int env_nomax = -1;  // IEF_TC3_NOMAX=0: always the exact running-maximum loop (A/B)
+  if (env_nomax < 0) { const char* e = getenv("IEF_TC3_NOMAX"); env_nomax = (e && e[0] == '0') ? 0 : 1; }
+  a.nomax = (env_nomax && p->dtype == IEF_BF16 && a.key_bias == nullptr) ? 1 : 0;
   a.scale_log2 = p->scale * kLog2e;
   a.rows = rows;
   a.dbg = ief_debug_trace_buffer();
@@ -439,7 +436,7 @@ int ief_attn_tc_launch(const ief_attn_params* p, const IefRowTable& rows, cudaSt
   if ((rc = make_map(&mv, p->dtype, p->v, p->d, p->Nk, p->H, p->B, a.perm_v)) != IEF_OK) return rc;
   // Kernel generations (IEF_TC_VERSION=1|2|3 caps the generation for A/B measurements):
   //   head_dim <= 64 : third generation (attn_tc3: column-split softmax, ordered exp sections), as 128-row split-KV CTAs when
-  //                    that shortens the estimated wave time, else as 256-row CTAs; generation 2: attn_tc2s / attn_tc2
+  //                    that shortens the estimated wave time, else as 256-row CTAs; generation 2: attn_tc2 (256-row CTAs only)
   //   head_dim <= 128: second generation (attn_tc2, P aliased onto S)        above: first generation (this file)
   static int env_version = -1;
   if (env_version < 0) { const char* e = getenv("IEF_TC_VERSION"); env_version = (e && e[0] >= '1' && e[0] <= '3') ? e[0] - '0' : 3; }
@@ -450,15 +447,12 @@ int ief_attn_tc_launch(const ief_attn_params* p, const IefRowTable& rows, cudaSt
   if (version >= 2 && dch == 1) {
     // 256-row CTAs (two query tiles share K/V) or 128-row CTAs (two key halves share Q)? Estimated time = waves x (key steps
     // per CTA + fixed prologue/epilogue, about three steps' worth): take the smaller. IEF_TC_SPLITKV=0|1|2 forces pair / split / hybrid.
-    static int force = -2, sms = 0;
+    static int force = -2;  // process-wide A/B switch read from the environment once; nothing device-dependent is cached here
     if (force == -2) {
       const char* e = getenv("IEF_TC_SPLITKV");
       force = e ? atoi(e) : -1;
-      int dev = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-      if (sms <= 0) sms = 148;
     }
+    const int sms = ief_sm_count();
     // estimated time in units of one key step: waves x (steps per CTA + ~3 steps of prologue/epilogue)
     const int nt = a.nt1 + a.nt2;
     const long pairs = (long)ief_ceil_div(p->Nq, 2 * kBM) * p->H * p->B;
@@ -472,9 +466,7 @@ int ief_attn_tc_launch(const ief_attn_params* p, const IefRowTable& rows, cudaSt
     else if (t_split < t_pair) mode = 1;
     if (version >= 3) {
       const int ntb = ief_ceil_div(p->Nk, kBN);
-      static int use_skip = -1;
-      if (use_skip < 0) { const char* e = getenv("IEF_TC3_SKIPMAX"); use_skip = e ? atoi(e) : 1; }
-      if ((use_skip == 2 || (use_skip == 1 && key_norm_prepass_pays(p))) && p->dtype == IEF_BF16 && p->workspace != nullptr && p->workspace_bytes >= (int64_t)p->B * p->H * ntb * (int64_t)sizeof(float)) {
+      if (key_norm_prepass_pays(p) && p->workspace != nullptr && p->workspace_bytes >= (int64_t)p->B * p->H * ntb * (int64_t)sizeof(float)) {
         IEF_REQUIRE((reinterpret_cast<uintptr_t>(p->workspace) & 15) == 0, IEF_ERR_INVALID, "ief_attn_fwd: workspace must be 16-byte aligned");
         float* kn = static_cast<float*>(p->workspace);
         key_norm_kernel<<<dim3(ntb, p->H, p->B), 128, 0, st>>>(static_cast<const __nv_bfloat16*>(p->k.ptr), p->k.stride_b, p->k.stride_n, p->k.stride_h,
@@ -485,7 +477,6 @@ int ief_attn_tc_launch(const ief_attn_params* p, const IefRowTable& rows, cudaSt
       }
       return ief_attn_tc3_launch(p, mq, mk, mv, a, mode, st);
     }
-    if (mode == 1) return ief_attn_tc2s_launch(p, mq, mk, mv, a, st);
   }
   if (version >= 2 && dch <= 2) return ief_attn_tc2_launch(p, mq, mk, mv, a, st);
   dim3 grid(ief_ceil_div(p->Nq, kBM), p->H, p->B);

@@ -380,11 +380,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 template <int DTYPE, int DCH>
 int launch_tc2(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const TcArgs& a, dim3 grid, cudaStream_t st) {
   auto kern = attn_tc2_kernel<DTYPE, DCH>;
-  static bool configured = false;
-  if (!configured) {
-    IEF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<DCH>::kSmemBytes));
-    configured = true;
-  }
+  IEF_CONFIG_SMEM(kern, Cfg2<DCH>::kSmemBytes);
   kern<<<grid, kThreads, Cfg2<DCH>::kSmemBytes, st>>>(mq, mk, mv, a);
   IEF_LAUNCH_OK("attn_tc2_kernel");
   return IEF_OK;

@@ -25,9 +25,19 @@
 // not the MUFU alone, so two compile-time variants delete instructions from it:
 //   SUMMMA  head_dim <= 48: row sums come from an extra [128 x 16] = P x ones MMA into the accumulator columns left free after O
 //           (same fp32 accumulation and lazy rescale as O) instead of 32 packed adds per row and tile
-//   SKIP    bf16 with a key-norm pre-pass (TcArgs::knorm): tiles whose Cauchy-Schwarz score bound is provably harmless skip the
-//           running-maximum pass, the exchange between the column halves and the rescale decision
-// (the same switches as run-time branches cost 8-13 %).
+//   MAXMODE 1 (SKIP)   bf16 with a key-norm pre-pass (TcArgs::knorm): tiles whose Cauchy-Schwarz score bound is provably harmless
+//           skip the running-maximum pass, the exchange between the column halves and the rescale decision (A/B only now)
+//   MAXMODE 2 (NOMAX)  bf16: OPTIMISTIC UNSHIFTED SOFTMAX. bf16 P and the fp32 accumulators carry 8 exponent bits, so
+//           P = exp2(scale*log2e*s) needs no running maximum at all while every row sum stays inside [2^-100, 2^100] - true for any
+//           attention logits within +-69 (natural units). The CTA runs its whole key loop without the maximum pass, the exchange
+//           between the column halves, the rescale decision and the shift, then looks at its row sums: in range -> normalise and
+//           store (the result is the softmax up to rounding: O/l is invariant to the reference point); out of range (inf, NaN,
+//           underflow) -> the SAME CTA repeats its key loop with the exact running-maximum loop (second pass; the mbarrier phase
+//           parities of that pass are offset by the number of phases the first pass completed, PbPass2). No pre-pass, no second
+//           launch; what the trace showed to bound the kernel - the serial chain load S -> max -> exchange -> decide -> scale ->
+//           waits between two exp sections of a stream (~1300-1500 clk against a 1024 clk exp section of the other stream) -
+//           shrinks to load S -> scale -> waits.
+// (the same switches as run-time branches inside one loop cost 8-13 %: the fast and the exact loop are separate instantiations.)
 #include "ief_common.cuh"
 #include "ptx_sm100.cuh"
 #include "attn_tc_host.cuh"
@@ -63,6 +73,30 @@ constexpr float kRescaleThreshold = 8.0f;
 // bf16 only: a tile whose Cauchy-Schwarz score bound stays within 2^kSkipMargin of the first tile's smallest row maximum needs no
 // row-maximum pass at all (P and the fp32 accumulators have 8 exponent bits; see the softmax section)
 constexpr float kSkipMargin = 80.0f;
+// MAXMODE 2: a row sum outside (2^-100, 2^100) sends the CTA into its exact second pass
+constexpr float kNoMaxLo = 7.8886090522101181e-31f, kNoMaxHi = 1.2676506002282294e+30f;
+#ifndef IEF_TC3_FAST_ORDERED
+#define IEF_TC3_FAST_ORDERED 1     // 0: the unshifted loop runs its exp sections unordered (A/B)
+#endif
+#ifndef IEF_TC3_FAST_SCALE_IN_TURN
+#define IEF_TC3_FAST_SCALE_IN_TURN 0  // 1: the scale multiply rides inside the exp section instead of before the turn (A/B)
+#endif
+constexpr bool kFastOrdered = IEF_TC3_FAST_ORDERED != 0;
+
+// mbarrier phase-parity bases of a pass: zero for the first (or only) pass; for the exact second pass of a MAXMODE 2 CTA the number
+// of phases each barrier completed during the first pass, mod 2
+struct PbZero {
+  __device__ __forceinline__ int stage(int) const { return 0; }
+  __device__ __forceinline__ int strm(int) const { return 0; }
+  __device__ __forceinline__ int turn(int) const { return 0; }
+};
+struct PbPass2 {
+  uint32_t m;  // bits 0..2: ring stages, 4..5: per-stream barriers (S, P, C, O), 6..7: exp-turn barriers
+  __device__ __forceinline__ int stage(int s) const { return (m >> s) & 1; }
+  __device__ __forceinline__ int strm(int t) const { return (m >> (4 + t)) & 1; }
+  __device__ __forceinline__ int turn(int t) const { return (m >> (6 + t)) & 1; }
+};
+template <bool V> struct BoolTag { static constexpr bool value = V; };
 
 template <bool SPLIT> struct Cfg3 {
   static constexpr int kQTiles = SPLIT ? 1 : 2;
@@ -76,13 +110,15 @@ __device__ __forceinline__ float approx_sqrt(float x) { float y; asm("sqrt.appro
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
-template <int DTYPE, bool SPLIT, int EMUL, bool SUMMMA, bool SKIP, bool BIAS>
+template <int DTYPE, bool SPLIT, int EMUL, bool SUMMMA, int MAXMODE, bool BIAS>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                 const __grid_constant__ TcArgs a) {
   using E = ElemT<DTYPE>;
   using Cfg = Cfg3<SPLIT>;
   constexpr int RT = Cfg::kRingTiles;
+  constexpr bool SKIP = MAXMODE == 1, NOMAX = MAXMODE == 2;
+  static_assert(!(NOMAX && BIAS), "the unshifted loop has no key-bias form");
   // 1-D grid over linearised work items so that a launch can cover any contiguous range of them (hybrid pair + split launches)
   const int lin = blockIdx.x + a.work_offset;
   const int qt = lin % a.nq_blocks;  // 256-row block (pair) or 128-row tile (split)
@@ -116,6 +152,7 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   auto bar_ve = [&](int s) { return bar0 + 88 + 8 * (3 * ST + s); };
   const uint32_t tmem_slot = bar0 + 88 + 32 * ST;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  volatile uint32_t* redo_flag = tmem_slot_ptr + 2;  // MAXMODE 2: some row sum of the unshifted pass left the safe range
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nt = a.nt1 + a.nt2;
@@ -131,6 +168,16 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     jj = blk2 ? g - a.nt1 : g;
     kb = blk2 ? a.rows.k2[b] : a.rows.k[b];
     vb = blk2 ? a.rows.v2[b] : a.rows.v[b];
+  };
+  // parity bases of the exact second pass (MAXMODE 2): phases completed by the first pass, per barrier
+  auto pass2_bases = [&]() {
+    PbPass2 pb;
+    pb.m = 0;
+#pragma unroll
+    for (int s = 0; s < ST; ++s) pb.m |= (uint32_t)((nt0 > s ? (nt0 - s + ST - 1) / ST : 0) & 1) << s;
+    pb.m |= (uint32_t)(nt0 & 1) << 4 | (uint32_t)(nt1 & 1) << 5;
+    if (kFastOrdered) pb.m |= (uint32_t)(nt1 & 1) << 6 | (uint32_t)(nt0 & 1) << 7;  // bar_x(t) completes once per section of stream t^1
+    return pb;
   };
 
   if (warp == 0 && lane == 0) {
@@ -151,6 +198,7 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(bar_vf(s), 1);
       mbar_init(bar_ve(s), 1);
     }
+    *redo_flag = 0;
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -172,17 +220,18 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot_ptr;
   if (cta_trace && threadIdx.x == 0) a.dbg[1537] = clock64();
 
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    reg_dec<kRegsLow>();
+  // ------------------------------------------------------------------ TMA producer (warp 0)
+  auto producer = [&](auto pb, bool load_q) {
     const int qb = a.rows.q[b];
-    if (elect_one()) {
-      mbar_arrive_expect_tx(bar_q, Cfg::kQTiles * kTile);
-      for (int t = 0; t < Cfg::kQTiles; ++t) tc_tma_tile(sQ(t), &tmQ, bar_q, 0, (Cfg::kQTiles * qt + t) * kBM, h, qb, a.perm_q);
+    if (load_q) {
+      if (elect_one()) {
+        mbar_arrive_expect_tx(bar_q, Cfg::kQTiles * kTile);
+        for (int t = 0; t < Cfg::kQTiles; ++t) tc_tma_tile(sQ(t), &tmQ, bar_q, 0, (Cfg::kQTiles * qt + t) * kBM, h, qb, a.perm_q);
+      }
+      __syncwarp();
     }
-    __syncwarp();
     for (int j = 0; j < nt0; ++j) {
-      const int s = j % ST, ph = (j / ST) & 1;
+      const int s = j % ST, ph = ((j / ST) + pb.stage(s)) & 1;
       const int nload = SPLIT ? (j < nt1 ? 2 : 1) : 1;
       mbar_wait(bar_ke(s), ph ^ 1);
       if (elect_one()) {
@@ -205,9 +254,10 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       __syncwarp();
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (whole warp waits, one elected lane issues)
-    reg_dec<kRegsLow>();
+  };
+
+  // ------------------------------------------------------------------ MMA issuer (warp 1: whole warp waits, one elected lane issues)
+  auto mma_issuer = [&](auto pb) {
     const uint64_t desc_k = make_smem_desc_sw128(0, 16, 1024);
     const uint64_t desc_v = make_smem_desc_sw128(0, kTcChunkBytes, 1024);
     auto issue_qk = [&](int t, int s) {
@@ -226,7 +276,7 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     };
     mbar_wait(bar_q, 0);
-    mbar_wait(bar_kf(0), 0);
+    mbar_wait(bar_kf(0), pb.stage(0));
     tc_fence_after();
     if (elect_one()) {
       issue_qk(0, 0);
@@ -235,14 +285,14 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     __syncwarp();
     for (int j = 0; j < nt0; ++j) {
-      const int s = j % ST, ph = (j / ST) & 1;
-      const int s1 = (j + 1) % ST, ph1 = ((j + 1) / ST) & 1;
+      const int s = j % ST, ph = ((j / ST) + pb.stage(s)) & 1;
+      const int s1 = (j + 1) % ST, ph1 = (((j + 1) / ST) + pb.stage(s1)) & 1;
       if (j + 1 < nt0) {  // next score tiles first: they only need S_t(j) to be in the softmax registers
         mbar_wait(bar_kf(s1), ph1);
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
           if (j + 1 < stream_nt(t)) {
-            mbar_wait(bar_c(t), j & 1);
+            mbar_wait(bar_c(t), (j + pb.strm(t)) & 1);
             tc_fence_after();
             if (elect_one()) issue_qk(t, s1);
             __syncwarp();
@@ -255,7 +305,7 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
         if (j < stream_nt(t)) {
-          mbar_wait(bar_p(t), j & 1);
+          mbar_wait(bar_p(t), (j + pb.strm(t)) & 1);
           tc_fence_after();
           if (elect_one()) {
             issue_pv(t, s, j > 0);
@@ -267,8 +317,20 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (elect_one()) umma_commit(bar_ve(s));
       __syncwarp();
     }
-  } else if (warp < 4) {
+  };
+
+  if (warp < 4) {
     reg_dec<kRegsLow>();
+    if (warp == 0) producer(PbZero{}, true);
+    else if (warp == 1) mma_issuer(PbZero{});
+    if constexpr (NOMAX) {
+      named_bar_sync(0, kThreads);  // the softmax warps have looked at the row sums of the unshifted pass
+      if (*redo_flag) {
+        const PbPass2 pb = pass2_bases();
+        if (warp == 0) producer(pb, false);
+        else if (warp == 1) mma_issuer(pb);
+      }
+    }
   } else {
     // ------------------------------------------------------------------ softmax of stream t, column half `half`
     reg_inc<kRegsHigh>();
@@ -311,183 +373,222 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int nchunk_o = (a.dv_mma >> 4) + (sum_mma ? 1 : 0);  // accumulator chunks touched by the lazy rescale (the row sums ride along in the chunk after O)
     const int my_nt = stream_nt(t);
 
+    // One pass over this stream's key tiles. FAST (MAXMODE 2, first pass): unshifted exponentials, no maximum, no exchange, no
+    // rescale. Otherwise the exact online softmax.
     // Turn protocol: exp sections alternate 0(0) 1(0) 0(1) 1(1) ...; stream 0 waits for stream 1's previous section, stream
     // 1 for stream 0's current one. In the split flavour stream 1 may be one step short (odd tile count): stream 0's last
     // grant then simply goes unused.
-    for (int j = 0; j < my_nt; ++j) {
-      int jj, kb_tile, vb_unused;
-      kv_coord(global_tile(t, j), jj, kb_tile, vb_unused);
-      const int vc = min(kBN, a.Nk - jj * kBN);
-      float kn_cur = 0.f;  // requested here, needed after the score load: its latency hides behind the barrier wait and tcgen05.ld
-      if constexpr (skip_guard) kn_cur = __ldg(a.knorm + ((int64_t)kb_tile * a.H + h) * a.knorm_tiles + jj);
+    auto run_pass = [&](auto fast_tag, auto pb) {
+      constexpr bool FAST = decltype(fast_tag)::value;
+      constexpr bool ordered = !FAST || kFastOrdered;
+      for (int j = 0; j < my_nt; ++j) {
+        int jj, kb_tile, vb_unused;
+        kv_coord(global_tile(t, j), jj, kb_tile, vb_unused);
+        const int vc = min(kBN, a.Nk - jj * kBN);
+        float kn_cur = 0.f;  // requested here, needed after the score load: its latency hides behind the barrier wait and tcgen05.ld
+        if constexpr (skip_guard && !FAST) kn_cur = __ldg(a.knorm + ((int64_t)kb_tile * a.H + h) * a.knorm_tiles + jj);
 #if IEF_TC3_TRACE
-      const bool trace = a.dbg != nullptr && lin == 0 && row == 0 && half == 0 && j < 64;
-      long long* tr = trace ? a.dbg + (t * 64 + j) * 8 : nullptr;
+        const bool trace = a.dbg != nullptr && lin == 0 && row == 0 && half == 0 && j < 64;
+        long long* tr = trace ? a.dbg + (t * 64 + j) * 8 : nullptr;
 #else
-      constexpr bool trace = false;
-      long long* tr = nullptr;
+        constexpr bool trace = false;
+        long long* tr = nullptr;
 #endif
 #if IEF_TC3_FINE_TRACE
-      long long* tr2 = trace ? a.dbg + 1024 + (t * 64 + j) * 4 : nullptr;  // sub-phases of the pre-turn work
+        long long* tr2 = trace ? a.dbg + 1024 + (t * 64 + j) * 4 : nullptr;  // sub-phases of the pre-turn work
 #endif
-      if (trace) tr[0] = clock64();
-      mbar_wait(bar_s(t), j & 1);
-      tc_fence_after();
-      if (trace) tr[1] = clock64();
-      uint32_t s0[32], s1[32];
-      tmem_ld32(tS, s0);
-      tmem_ld32(tS + 32, s1);
-      tc_wait_ld();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_c(t));  // S_t(j) is in registers: the tensor pipe may overwrite it with S_t(j+1)
-      if (trace) tr[2] = clock64();
-      if constexpr (BIAS) {
-        if (bias_row != nullptr) {
-          // masked keys carry finfo.min in the reference; clamped so that the product with log2(e) stays finite and a row whose keys
-          // are all masked still comes out as the uniform average, as it does there. Out-of-range columns are masked below.
-          const float* bp = bias_row + jj * kBN + 64 * half;
-          const float sl = a.scale_log2;
+        if (trace) tr[0] = clock64();
+        mbar_wait(bar_s(t), (j + pb.strm(t)) & 1);
+        tc_fence_after();
+        if (trace) tr[1] = clock64();
+        uint32_t s0[32], s1[32];
+        tmem_ld32(tS, s0);
+        tmem_ld32(tS + 32, s1);
+        tc_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_c(t));  // S_t(j) is in registers: the tensor pipe may overwrite it with S_t(j+1)
+        if (trace) tr[2] = clock64();
+        if constexpr (BIAS) {
+          if (bias_row != nullptr) {
+            // masked keys carry finfo.min in the reference; clamped so that the product with log2(e) stays finite and a row whose keys
+            // are all masked still comes out as the uniform average, as it does there. Out-of-range columns are masked below.
+            const float* bp = bias_row + jj * kBN + 64 * half;
+            const float sl = a.scale_log2;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float b0 = 64 * half + i < vc ? fmaxf(__ldg(bp + i) * 1.4426950408889634f, -3.0e38f) : 0.f;
-            const float b1 = 64 * half + 32 + i < vc ? fmaxf(__ldg(bp + 32 + i) * 1.4426950408889634f, -3.0e38f) : 0.f;
-            s0[i] = __float_as_uint(fmaf(__uint_as_float(s0[i]), sl, b0));
-            s1[i] = __float_as_uint(fmaf(__uint_as_float(s1[i]), sl, b1));
+            for (int i = 0; i < 32; ++i) {
+              const float b0 = 64 * half + i < vc ? fmaxf(__ldg(bp + i) * 1.4426950408889634f, -3.0e38f) : 0.f;
+              const float b1 = 64 * half + 32 + i < vc ? fmaxf(__ldg(bp + 32 + i) * 1.4426950408889634f, -3.0e38f) : 0.f;
+              s0[i] = __float_as_uint(fmaf(__uint_as_float(s0[i]), sl, b0));
+              s1[i] = __float_as_uint(fmaf(__uint_as_float(s1[i]), sl, b1));
+            }
           }
         }
-      }
-      if (vc < kBN) {
-        mask_chunk(s0, 64 * half, vc);
-        mask_chunk(s1, 64 * half + 32, vc);
-      }
-      bool o_ready = j == 0;
-      // bf16: P and the fp32 accumulators carry 8 exponent bits, so the running maximum only has to keep exp2() in range, not
-      // near 1. qn_max * kn(tile) * c2 bounds every scaled score of the tile (Cauchy-Schwarz); while it stays within
-      // 2^kSkipMargin of the smallest first-tile row maximum, m_used is left alone and the tile needs no maximum pass, no
-      // exchange between the column halves and no rescale decision. The test is identical in all 256 threads of the stream.
-      bool exact = true;
-      if constexpr (skip_guard) exact = j == 0 || qn_max * kn_cur * c2 - m_floor > kSkipMargin;
-      if (exact) {
-        // row maximum: own 64 columns, then exchange with the other half of the row
-        const float lmax = fmaxf(max_chunk(s0, -INFINITY), max_chunk(s1, -INFINITY));
+        if (vc < kBN) {
+          mask_chunk(s0, 64 * half, vc);
+          mask_chunk(s1, 64 * half + 32, vc);
+        }
+        bool o_ready = j == 0;
+        if constexpr (!FAST) {
+          // bf16: P and the fp32 accumulators carry 8 exponent bits, so the running maximum only has to keep exp2() in range, not
+          // near 1. qn_max * kn(tile) * c2 bounds every scaled score of the tile (Cauchy-Schwarz); while it stays within
+          // 2^kSkipMargin of the smallest first-tile row maximum, m_used is left alone and the tile needs no maximum pass, no
+          // exchange between the column halves and no rescale decision. The test is identical in all 256 threads of the stream.
+          bool exact = true;
+          if constexpr (skip_guard) exact = j == 0 || qn_max * kn_cur * c2 - m_floor > kSkipMargin;
+          if (exact) {
+            // row maximum: own 64 columns, then exchange with the other half of the row
+            const float lmax = fmaxf(max_chunk(s0, -INFINITY), max_chunk(s1, -INFINITY));
 #if IEF_TC3_FINE_TRACE
-        if (trace) tr2[0] = clock64();
+            if (trace) tr2[0] = clock64();
 #endif
-        float* xm = xmax + ((j & 1) * 4 + t * 2) * 128;
-        xm[half * 128 + row] = lmax;
-        named_bar_sync(1 + t, 256);
-#if IEF_TC3_FINE_TRACE
-        if (trace) tr2[1] = clock64();
-#endif
-        const float tmax = fmaxf(lmax, xm[(half ^ 1) * 128 + row]);
-        if (j == 0) {
-          m_used = tmax;
-          if constexpr (skip_guard) {
-            // one-time: stream-wide max |q_row| and min first-tile row maximum through shared memory
-            float qn = qn_row, mf = tmax * c2;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-              qn = fmaxf(qn, __shfl_xor_sync(0xffffffffu, qn, o));
-              mf = fminf(mf, __shfl_xor_sync(0xffffffffu, mf, o));
-            }
-            float* xw = xq + t * 16;
-            if (lane == 0) {
-              xw[2 * (idx & 7)] = qn;
-              xw[2 * (idx & 7) + 1] = mf;
-            }
+            float* xm = xmax + ((j & 1) * 4 + t * 2) * 128;
+            xm[half * 128 + row] = lmax;
             named_bar_sync(1 + t, 256);
-            qn_max = xw[0];
-            m_floor = xw[1];
+#if IEF_TC3_FINE_TRACE
+            if (trace) tr2[1] = clock64();
+#endif
+            const float tmax = fmaxf(lmax, xm[(half ^ 1) * 128 + row]);
+            if (j == 0) {
+              m_used = tmax;
+              if constexpr (skip_guard) {
+                // one-time: stream-wide max |q_row| and min first-tile row maximum through shared memory
+                float qn = qn_row, mf = tmax * c2;
 #pragma unroll
-            for (int w8 = 1; w8 < 8; ++w8) {
-              qn_max = fmaxf(qn_max, xw[2 * w8]);
-              m_floor = fminf(m_floor, xw[2 * w8 + 1]);
-            }
-          }
-        } else {
-          const float m_new = fmaxf(m_used, tmax);
-          const bool need = (m_new - m_used) * c2 > kRescaleThreshold;
-          if (__any_sync(0xffffffffu, need)) {  // both halves of a row see identical values and take the same decision
-            mbar_wait(bar_o(t), (j - 1) & 1);
-            tc_fence_after();
-            o_ready = true;
-            const float alpha = ief_exp2((m_used - m_new) * c2);
-            for (int cc = half; cc < nchunk_o; cc += 2) {  // this half's share of the O columns
-              uint32_t r[16];
-              tmem_ld16(tO + 16 * cc, r);
-              tc_wait_ld();
+                for (int o = 16; o > 0; o >>= 1) {
+                  qn = fmaxf(qn, __shfl_xor_sync(0xffffffffu, qn, o));
+                  mf = fminf(mf, __shfl_xor_sync(0xffffffffu, mf, o));
+                }
+                float* xw = xq + t * 16;
+                if (lane == 0) {
+                  xw[2 * (idx & 7)] = qn;
+                  xw[2 * (idx & 7) + 1] = mf;
+                }
+                named_bar_sync(1 + t, 256);
+                qn_max = xw[0];
+                m_floor = xw[1];
 #pragma unroll
-              for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-              tmem_st16(tO + 16 * cc, r);
+                for (int w8 = 1; w8 < 8; ++w8) {
+                  qn_max = fmaxf(qn_max, xw[2 * w8]);
+                  m_floor = fminf(m_floor, xw[2 * w8 + 1]);
+                }
+              }
+            } else {
+              const float m_new = fmaxf(m_used, tmax);
+              const bool need = (m_new - m_used) * c2 > kRescaleThreshold;
+              if (__any_sync(0xffffffffu, need)) {  // both halves of a row see identical values and take the same decision
+                mbar_wait(bar_o(t), (j - 1 + pb.strm(t)) & 1);
+                tc_fence_after();
+                o_ready = true;
+                const float alpha = ief_exp2((m_used - m_new) * c2);
+                for (int cc = half; cc < nchunk_o; cc += 2) {  // this half's share of the O columns
+                  uint32_t r[16];
+                  tmem_ld16(tO + 16 * cc, r);
+                  tc_wait_ld();
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+                  tmem_st16(tO + 16 * cc, r);
+                }
+                l *= alpha;
+                m_used = m_new;
+              }
             }
-            l *= alpha;
-            m_used = m_new;
           }
         }
+#if IEF_TC3_FINE_TRACE
+        if (trace) tr2[2] = clock64();
+#endif
+        const float mc = FAST ? 0.f : m_used * c2;
+        const float2 c2v = make_float2(c2, c2), nmc = make_float2(-mc, -mc);
+        constexpr bool scale_in_turn = FAST && IEF_TC3_FAST_SCALE_IN_TURN;
+        if constexpr (!scale_in_turn) {
+          scale_chunk_mix<EMUL>(s0, c2v, nmc);   // FMA-pipe work (incl. the emulated share of the exponentials), outside the MUFU turn
+          scale_chunk_mix<EMUL>(s1, c2v, nmc);
+        }
+#if IEF_TC3_FINE_TRACE
+        if (trace) tr[6] = clock64();
+#endif
+        if (!o_ready) {  // PV_t(j-1) must have finished reading P_t; wait for it BEFORE taking the exp turn, not inside it
+          mbar_wait(bar_o(t), (j - 1 + pb.strm(t)) & 1);
+          tc_fence_after();
+        }
+#if IEF_TC3_FINE_TRACE
+        if (trace) tr[7] = clock64();
+#endif
+        if constexpr (ordered) {
+          if (t == 1 || j > 0) mbar_wait(bar_x(t), ((t == 1 ? j : j - 1) + pb.turn(t)) & 1);   // ordered exp sections
+        }
+        if (trace) tr[3] = clock64();
+        float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+        uint32_t u[16];
+        if constexpr (scale_in_turn) scale_chunk_mix<EMUL>(s0, c2v, nmc);
+        if constexpr (sum_mma) exp_pack_chunk_nosum<E, EMUL>(s0, u); else exp_pack_chunk_mix<E, EMUL>(s0, u, acc0, acc1);
+        tmem_st16(tP, u);
+#if !IEF_TC3_HANDOVER_LATE
+        if constexpr (ordered) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_x(t ^ 1));  // hand the MUFU over one chunk early
+        }
+#endif
+        if constexpr (scale_in_turn) scale_chunk_mix<EMUL>(s1, c2v, nmc);
+        if constexpr (sum_mma) exp_pack_chunk_nosum<E, EMUL>(s1, u); else exp_pack_chunk_mix<E, EMUL>(s1, u, acc0, acc1);
+        tmem_st16(tP + 16, u);
+#if IEF_TC3_HANDOVER_LATE
+        if constexpr (ordered) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_x(t ^ 1));
+        }
+#endif
+        if (trace) tr[4] = clock64();
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(bar_p(t));
+        if (trace) tr[5] = clock64();
+        if constexpr (!sum_mma) {
+          acc0 = fadd2(acc0, acc1);
+          l += acc0.x + acc0.y;
+        }
       }
-#if IEF_TC3_FINE_TRACE
-      if (trace) tr2[2] = clock64();
-#endif
-      const float mc = m_used * c2;
-      const float2 c2v = make_float2(c2, c2), nmc = make_float2(-mc, -mc);
-      scale_chunk_mix<EMUL>(s0, c2v, nmc);   // FMA-pipe work (incl. the emulated share of the exponentials), outside the MUFU turn
-      scale_chunk_mix<EMUL>(s1, c2v, nmc);
-#if IEF_TC3_FINE_TRACE
-      if (trace) tr[6] = clock64();
-#endif
-      if (!o_ready) {  // PV_t(j-1) must have finished reading P_t; wait for it BEFORE taking the exp turn, not inside it
-        mbar_wait(bar_o(t), (j - 1) & 1);
+      if (cta_trace && warp == 4 && lane == 0) a.dbg[1538] = clock64();
+      if (my_nt > 0) {
+        mbar_wait(bar_o(t), (my_nt - 1 + pb.strm(t)) & 1);
         tc_fence_after();
       }
-#if IEF_TC3_FINE_TRACE
-      if (trace) tr[7] = clock64();
-#endif
-      if (t == 1 || j > 0) mbar_wait(bar_x(t), (t == 1 ? j : j - 1) & 1);   // ordered exp sections
-      if (trace) tr[3] = clock64();
-      float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
-      uint32_t u[16];
-      if constexpr (sum_mma) exp_pack_chunk_nosum<E, EMUL>(s0, u); else exp_pack_chunk_mix<E, EMUL>(s0, u, acc0, acc1);
-      tmem_st16(tP, u);
-#if !IEF_TC3_HANDOVER_LATE
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_x(t ^ 1));  // hand the MUFU over one chunk early
-#endif
-      if constexpr (sum_mma) exp_pack_chunk_nosum<E, EMUL>(s1, u); else exp_pack_chunk_mix<E, EMUL>(s1, u, acc0, acc1);
-      tmem_st16(tP + 16, u);
-#if IEF_TC3_HANDOVER_LATE
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_x(t ^ 1));
-#endif
-      if (trace) tr[4] = clock64();
-      tc_wait_st();
-      tc_fence_before();
-      mbar_arrive(bar_p(t));
-      if (trace) tr[5] = clock64();
-      if constexpr (!sum_mma) {
-        acc0 = fadd2(acc0, acc1);
-        l += acc0.x + acc0.y;
+      if (cta_trace && warp == 4 && lane == 0) a.dbg[1539] = clock64();
+    };
+    // row sum = first accumulator column after O (row-sum MMA) or the merge of the two column halves' partial sums
+    auto row_sum = [&]() -> float {
+      if constexpr (sum_mma) {
+        uint32_t r[16];
+        tmem_ld16(tO + a.dv_mma, r);
+        tc_wait_ld();
+        return my_nt > 0 ? __uint_as_float(r[0]) : 0.f;
+      } else {
+        float* xs = xsum + t * 2 * 128;
+        xs[half * 128 + row] = l;
+        named_bar_sync(1 + t, 256);
+        return l + xs[(half ^ 1) * 128 + row];
       }
-    }
-    if (cta_trace && warp == 4 && lane == 0) a.dbg[1538] = clock64();
-    if (my_nt > 0) {
-      mbar_wait(bar_o(t), (my_nt - 1) & 1);
-      tc_fence_after();
-    }
-    if (cta_trace && warp == 4 && lane == 0) a.dbg[1539] = clock64();
-    // ---- epilogue: row sum = first accumulator column after O (row-sum MMA) or the merge of the two column halves' partial sums ...
+    };
+
     float lrow;
-    if constexpr (sum_mma) {
-      uint32_t r[16];
-      tmem_ld16(tO + a.dv_mma, r);
-      tc_wait_ld();
-      lrow = my_nt > 0 ? __uint_as_float(r[0]) : 0.f;
+    if constexpr (NOMAX) {
+      m_used = 0.f;
+      run_pass(BoolTag<true>{}, PbZero{});
+      lrow = row_sum();
+      if (my_nt > 0 && !(lrow > kNoMaxLo && lrow < kNoMaxHi)) *redo_flag = 1;  // inf, NaN, zero or close to the edge of the fp32 / bf16 range
+      named_bar_sync(0, kThreads);
+      if (*redo_flag) {
+        m_used = -INFINITY;
+        l = 0.f;
+        run_pass(BoolTag<false>{}, pass2_bases());
+        lrow = row_sum();
+      }
     } else {
-      float* xs = xsum + t * 2 * 128;
-      xs[half * 128 + row] = l;
-      named_bar_sync(1 + t, 256);
-      lrow = l + xs[(half ^ 1) * 128 + row];
+      run_pass(BoolTag<false>{}, PbZero{});
+      lrow = row_sum();
     }
+    // ---- epilogue
     const int nchunk_d = (a.d + 15) >> 4;
     float wmine = 1.f, wother = 0.f;
     if constexpr (SPLIT) {
@@ -557,14 +658,10 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (cta_trace && threadIdx.x == 32) a.dbg[1541] = clock64();
 }
 
-template <int DTYPE, bool SPLIT, bool SUMMMA, bool SKIP, bool BIAS = false>
+template <int DTYPE, bool SPLIT, bool SUMMMA, int MAXMODE, bool BIAS = false>
 int launch_tc3s(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, TcArgs a, int first, int count, int nq_blocks, cudaStream_t st) {
-  auto kern = attn_tc3_kernel<DTYPE, SPLIT, kDefaultEmul, SUMMMA, SKIP, BIAS>;
-  static bool configured = false;
-  if (!configured) {
-    IEF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg3<SPLIT>::kSmemBytes));
-    configured = true;
-  }
+  auto kern = attn_tc3_kernel<DTYPE, SPLIT, kDefaultEmul, SUMMMA, MAXMODE, BIAS>;
+  IEF_CONFIG_SMEM(kern, Cfg3<SPLIT>::kSmemBytes);
   if (count <= 0) return IEF_OK;
   a.work_offset = first;
   a.nq_blocks = nq_blocks;
@@ -576,15 +673,18 @@ int launch_tc3s(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap&
 template <int DTYPE, bool SPLIT>
 int launch_tc3(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, TcArgs a, int first, int count, int nq_blocks, cudaStream_t st) {
   if (a.key_bias != nullptr)  // masked MasaCtrl passes: the variant that adds a per-key bias before the maximum
-    return a.sum_mma ? launch_tc3s<DTYPE, SPLIT, true, false, true>(mq, mk, mv, a, first, count, nq_blocks, st)
-                     : launch_tc3s<DTYPE, SPLIT, false, false, true>(mq, mk, mv, a, first, count, nq_blocks, st);
+    return a.sum_mma ? launch_tc3s<DTYPE, SPLIT, true, 0, true>(mq, mk, mv, a, first, count, nq_blocks, st)
+                     : launch_tc3s<DTYPE, SPLIT, false, 0, true>(mq, mk, mv, a, first, count, nq_blocks, st);
   if constexpr (DTYPE == IEF_BF16) {
-    if (a.knorm != nullptr)  // key-norm pre-pass available: the variant that skips provably harmless row-maximum passes
-      return a.sum_mma ? launch_tc3s<DTYPE, SPLIT, true, true>(mq, mk, mv, a, first, count, nq_blocks, st)
-                       : launch_tc3s<DTYPE, SPLIT, false, true>(mq, mk, mv, a, first, count, nq_blocks, st);
+    if (a.knorm != nullptr)  // key-norm pre-pass available: the variant that skips provably harmless row-maximum passes (A/B only)
+      return a.sum_mma ? launch_tc3s<DTYPE, SPLIT, true, 1>(mq, mk, mv, a, first, count, nq_blocks, st)
+                       : launch_tc3s<DTYPE, SPLIT, false, 1>(mq, mk, mv, a, first, count, nq_blocks, st);
+    if (a.nomax)             // optimistic unshifted softmax with the in-CTA exact second pass
+      return a.sum_mma ? launch_tc3s<DTYPE, SPLIT, true, 2>(mq, mk, mv, a, first, count, nq_blocks, st)
+                       : launch_tc3s<DTYPE, SPLIT, false, 2>(mq, mk, mv, a, first, count, nq_blocks, st);
   }
-  return a.sum_mma ? launch_tc3s<DTYPE, SPLIT, true, false>(mq, mk, mv, a, first, count, nq_blocks, st)
-                   : launch_tc3s<DTYPE, SPLIT, false, false>(mq, mk, mv, a, first, count, nq_blocks, st);
+  return a.sum_mma ? launch_tc3s<DTYPE, SPLIT, true, 0>(mq, mk, mv, a, first, count, nq_blocks, st)
+                   : launch_tc3s<DTYPE, SPLIT, false, 0>(mq, mk, mv, a, first, count, nq_blocks, st);
 }
 
 template <int DTYPE>
@@ -594,13 +694,7 @@ int launch_mode(const ief_attn_params* p, const CUtensorMap& mq, const CUtensorM
   if (mode == 0) return launch_tc3<DTYPE, false>(mq, mk, mv, a, 0, pairs, nqp, st);
   if (mode == 1) return launch_tc3<DTYPE, true>(mq, mk, mv, a, 0, 2 * pairs, 2 * nqp, st);
   // hybrid: the full waves as 256-row CTAs, the remaining r < #SM/2 pairs as 2r half-length split-KV CTAs (pair L = split 2L, 2L+1)
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
+  const int sms = ief_sm_count();
   const int full = (pairs / sms) * sms, rest = pairs - full;
   int rc = launch_tc3<DTYPE, false>(mq, mk, mv, a, 0, full, nqp, st);
   if (rc != IEF_OK) return rc;

@@ -16,6 +16,7 @@ struct TcArgs {
   uint32_t idesc_qk, idesc_pv;
   uint32_t idesc_sum;      // attn_tc3: [128 x 16] = P x ones (row sums on the tensor pipe), K-major B operand
   int32_t sum_mma;         // attn_tc3: 1 when dv_mma <= 48: the 16 columns after O in each 64-column accumulator hold the row sums
+  int32_t nomax;           // attn_tc3, bf16: optimistic unshifted softmax with an in-CTA exact second pass (MAXMODE 2)
   float scale_log2;
   int32_t perm_q[3], perm_k[3], perm_v[3];  // which of (token, head, row) feeds TMA coordinate 1..3
   int32_t work_offset;  // attn_tc3: first linear work item (q block + nq_blocks * (head + H * row)) of this launch
@@ -39,5 +40,4 @@ long long* ief_debug_trace_buffer();
 int ief_tc_make_map(CUtensorMap* m, int dtype, const ief_tensor4& t, int d, int N, int H, int B, int32_t perm[3], int box_rows);
 int ief_attn_tc3_launch(const ief_attn_params* p, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const TcArgs& a, int mode,
                         cudaStream_t st);  // mode: 0 pair, 1 split, 2 hybrid (full waves as pairs, remainder split)
-int ief_attn_tc2s_launch(const ief_attn_params* p, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const TcArgs& a, cudaStream_t st);
 int ief_attn_tc2_launch(const ief_attn_params* p, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const TcArgs& a, cudaStream_t st);

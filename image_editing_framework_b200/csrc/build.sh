@@ -11,11 +11,11 @@ FLAGS+=("${EXTRA[@]}")
 objs=()
 pids=()
 mkdir -p "$here/build"
-for f in api attn_tc attn_tc2 attn_tc2s attn_tc3 attn_mma cross_attn cross_tc cross_attn_bwd elementwise; do
+for f in api attn_tc attn_tc2 attn_tc3 attn_mma cross_attn cross_tc cross_attn_bwd elementwise; do
   "$NVCC" "${FLAGS[@]}" -c "$here/$f.cu" -o "$here/build/$f.o" &
   pids+=($!)
   objs+=("$here/build/$f.o")
 done
 for p in "${pids[@]}"; do wait "$p"; done
-"$NVCC" -shared -o "$out/libief_b200.so" "${objs[@]}" -lcudart_static -ldl -lrt -lpthread
+"$NVCC" -shared -o "$out/libief_b200.so" "${objs[@]}" -Xlinker --no-undefined -lcudart_static -lcuda -ldl -lrt -lpthread
 echo "built $out/libief_b200.so"

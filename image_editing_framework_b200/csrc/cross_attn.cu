@@ -264,11 +264,7 @@ template <int DTYPE, int DP, int FLAVOUR>
 int launch_one(const CrossArgs& a, dim3 grid, cudaStream_t st) {
   constexpr int smem = cross_smem_bytes<FLAVOUR, DP>();
   auto kern = cross_attn_edit_kernel<DTYPE, DP, FLAVOUR>;
-  static bool configured = false;
-  if (!configured) {
-    IEF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
+  IEF_CONFIG_SMEM(kern, smem);
   kern<<<grid, kThreads, smem, st>>>(a);
   IEF_LAUNCH_OK("cross_attn_edit_kernel");
   return IEF_OK;

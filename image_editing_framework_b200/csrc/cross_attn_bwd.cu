@@ -185,11 +185,7 @@ template <int DTYPE, int DP>
 int launch_one(const BwdArgs& a, dim3 grid, cudaStream_t st) {
   constexpr int smem = 2 * (kBM + kNKP) * (DP + 8) * 2;
   auto kern = cross_attn_bwd_kernel<DTYPE, DP>;
-  static bool configured = false;
-  if (!configured) {
-    IEF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
+  IEF_CONFIG_SMEM(kern, smem);
   kern<<<grid, kThreads, smem, st>>>(a);
   IEF_LAUNCH_OK("cross_attn_bwd_kernel");
   return IEF_OK;

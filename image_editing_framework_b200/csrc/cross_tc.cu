@@ -207,11 +207,7 @@ cross_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 template <int DTYPE, int DCH, int TCOLS>
 int launch_cross_tc(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CrossTcArgs& a, dim3 grid, cudaStream_t st) {
   auto kern = cross_tc_kernel<DTYPE, DCH, TCOLS>;
-  static bool configured = false;
-  if (!configured) {
-    IEF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cross_tc_smem<DCH>()));
-    configured = true;
-  }
+  IEF_CONFIG_SMEM(kern, cross_tc_smem<DCH>());
   kern<<<grid, kThreads, cross_tc_smem<DCH>(), st>>>(mq, mk, mv, a);
   IEF_LAUNCH_OK("cross_tc_kernel");
   return IEF_OK;
@@ -245,13 +241,7 @@ int ief_cross_tc_launch(const ief_cross_params* p, cudaStream_t st) {
   const int cfg = p->d <= 48 ? 0 : (p->d <= 64 ? 1 : (p->d <= 128 ? 2 : 3));  // (chunks, TMEM columns): (1,128) (1,256) (2,256) (3,256)
   // One wave: as many consecutive query tiles per CTA as it takes for all CTAs to be resident at once (4 per SM at 128 TMEM
   // columns, 2 at 256); the per-CTA prologue (barriers, TMEM allocation, K/V load) is then paid once per 1-8 tiles.
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
+  const int sms = ief_sm_count();
   const int nqt = ief_ceil_div(p->Nq, kBM);
   const long slots = (long)sms * (cfg == 0 ? 4 : 2);
   int tpc = (int)(((long)nqt * p->H * p->B + slots - 1) / slots);

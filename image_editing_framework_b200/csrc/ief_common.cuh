@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <atomic>
 
 #include "../../include/ief_b200.h"
 
@@ -85,6 +86,36 @@ __device__ __forceinline__ float ief_exp2(float x) {
 }
 
 static inline int ief_ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ---- per-device launch configuration ---------------------------------------------------------------
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a property of (kernel, device): one process may drive several GPUs, so the
+// "already configured" memo is a bit per device ordinal and per call site (= per kernel template instance), never per process.
+#define IEF_CONFIG_SMEM(kern, bytes)                                                                                   \
+  do {                                                                                                                 \
+    static std::atomic<uint64_t> done__[4];                                                                            \
+    int dev__ = 0;                                                                                                     \
+    IEF_CUDA_OK(cudaGetDevice(&dev__));                                                                                \
+    const uint64_t bit__ = 1ull << (dev__ & 63);                                                                       \
+    std::atomic<uint64_t>& w__ = done__[(dev__ >> 6) & 3];                                                             \
+    if (!(w__.load(std::memory_order_acquire) & bit__)) {                                                              \
+      IEF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));              \
+      w__.fetch_or(bit__, std::memory_order_release);                                                                  \
+    }                                                                                                                  \
+  } while (0)
+
+// SM count of the CURRENT device (cached per device ordinal; 148 on B200)
+static inline int ief_sm_count() {
+  static std::atomic<int> cache[256];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  std::atomic<int>& c = cache[dev & 255];
+  int n = c.load(std::memory_order_relaxed);
+  if (n <= 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    c.store(n, std::memory_order_relaxed);
+  }
+  return n;
+}
 
 // internal launchers (one per .cu)
 int ief_attn_mma_launch(const ief_attn_params* p, const IefRowTable& rows, cudaStream_t st);

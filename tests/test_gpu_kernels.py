@@ -155,6 +155,44 @@ def test_attn_tcgen05_max_skipping_guard(cuda, case):
     assert err < TOL, f"{case}: max abs err {err}"
 
 
+@pytest.mark.parametrize("shape", [
+    (2, 2, 640, 3200, 64),     # 128-row split-KV CTAs, row sums in registers
+    (2, 2, 640, 1100, 40),     # split-KV, odd number of key tiles (stream 1 one step short), row-sum MMA
+    (2, 8, 2560, 1024, 40),    # 256-row pair CTAs (+ hybrid remainder), row-sum MMA
+    (2, 10, 2304, 2304, 64),   # pair CTAs, row sums in registers
+])
+@pytest.mark.parametrize("case", ["plain", "overflow", "underflow", "one_batch_row", "few_query_rows", "union"])
+def test_attn_tcgen05_unshifted_softmax_second_pass(cuda, shape, case):
+    """bf16: the kernel first runs its key loop WITHOUT a running maximum (P = exp2(scaled score), attn_tc3 MAXMODE 2) and
+    repeats it with the exact online softmax inside the same CTA when a row sum leaves (2^-100, 2^100). Same softmax either way:
+    (a) ordinary data (first pass only), (b) scores far above 2^127 -> inf row sums, (c) every score of some rows below -200
+    -> zero row sums, (d) only one batch row overflows (other CTAs keep their first pass), (e) a handful of peaked query rows,
+    (f) two key/value blocks with overflow."""
+    B, H, N, M, d = shape
+    q, k, v = _qkv(B, N, M, H, d, 57 + N)
+    q, k = q.float(), k.float()
+    if case in ("overflow", "union"):
+        q, k = q * 7, k * 7
+    elif case == "underflow":
+        q[..., 0::d], k[..., 0::d] = 48.0, -48.0        # channel 0 of every head: -2304 * scale on every score
+    elif case == "one_batch_row":
+        q[1], k[1] = q[1] * 7, k[1] * 7
+    elif case == "few_query_rows":
+        q[:, 5::97] *= 60
+    q, k = q.to(torch.bfloat16), k.to(torch.bfloat16)
+    kw = {}
+    if case == "union":
+        kw = dict(k_src=[0] * B, v_src=[0] * B, k_src2=list(range(B)), v_src2=list(range(B)))
+    scale = d ** -0.5
+    want = orc.indexed_attention(q, k, v, H, scale, **kw)
+    got = ops.attention(q.to(cuda), k.to(cuda), v.to(cuda), H, scale, impl=ops.IEF_IMPL_TCGEN05, **kw)
+    torch.cuda.synchronize()
+    assert _cabi.last_attn_impl() == "tcgen05"
+    assert torch.isfinite(got).all(), f"{case}: non-finite output"
+    err = (got.float().cpu() - want).abs().max().item()
+    assert err < TOL, f"{case} {shape}: max abs err {err}"
+
+
 def test_attn_auto_dispatch(cuda):
     q, k, v = _qkv(2, 4096, 4096, 8, 40, 0)
     ops.attention(q.to(cuda), k.to(cuda), v.to(cuda), 8, 40 ** -0.5)
@@ -423,8 +461,9 @@ def test_full_size_properties(cuda, name, B, H, N, d):
 
 
 def test_attn_workspace_contract(cuda):
-    """ief_attn_workspace_bytes: non-zero only where the key-norm pre-pass pays (bf16, head_dim 49-64, >= 24 key tiles); a call
-    without workspace, with too small a workspace, or with the pre-pass gives the same softmax."""
+    """ief_attn_workspace_bytes: zero for plain calls (the key-norm pre-pass is an A/B option since the unshifted loop replaced
+    it: IEF_TC3_SKIPMAX=2), B*H*Nq floats for stored maps behind a tcgen05 launch; a call without workspace, with too small a
+    workspace, or with one gives the same softmax."""
     import ctypes as C
     B, H, N, d = 1, 2, 3200, 64
     q, k, v = (t.to(cuda) for t in _qkv(B, N, N, H, d, 41))
@@ -442,10 +481,14 @@ def test_attn_workspace_contract(cuda):
     lib = _cabi.lib()
     p = params(q, k, v, d)
     need = lib.ief_attn_workspace_bytes(C.byref(p))
-    assert need == B * H * 25 * 4
+    forced = os.environ.get("IEF_TC3_SKIPMAX") == "2"
+    assert need == (B * H * 25 * 4 if forced else 0)
+    need = B * H * 25 * 4   # what the A/B pre-pass would take: offering it must never change the result
     q40 = q[..., :H * 40].contiguous()
-    assert lib.ief_attn_workspace_bytes(C.byref(params(q40, q40, q40, 40))) == 0            # head_dim 40: row-sum MMA variant instead
-    assert lib.ief_attn_workspace_bytes(C.byref(params(q[:, :1024], k[:, :1024], v[:, :1024], d))) == 0   # 8 key tiles: too short
+    if not forced:
+        assert lib.ief_attn_workspace_bytes(C.byref(params(q40, q40, q40, 40))) == 0
+    if not forced:
+        assert lib.ief_attn_workspace_bytes(C.byref(params(q[:, :1024], k[:, :1024], v[:, :1024], d))) == 0
     qh = q.to(torch.float16)
     assert lib.ief_attn_workspace_bytes(C.byref(params(qh, qh, qh, d))) == 0                # fp16 keeps the exact maximum
     stream = torch.cuda.current_stream().cuda_stream

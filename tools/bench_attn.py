@@ -33,8 +33,12 @@ def main():
         ("big_d64", 8, 16, 4096, 64), ("big_d40", 16, 8, 4096, 40),
     ]
     impls = [("tcgen05", ops.IEF_IMPL_TCGEN05), ("mma", ops.IEF_IMPL_MMA)]
-    if len(sys.argv) > 1:
-        impls = [i for i in impls if i[0] in sys.argv[1:]]
+    args = sys.argv[1:]
+    if any(a in ("tcgen05", "mma") for a in args):
+        impls = [i for i in impls if i[0] in args]
+    if "big" in args:   # the six large shapes only
+        shapes = [s_ for s_ in shapes if s_[0] in ("sd15_64", "sd21_96", "sd21_48", "sdxl_64", "sdxl_32", "big_d64", "big_d40")]
+    no_sdpa = "nosdpa" in args
     out = []
     for name, B, H, N, d in shapes:
         q, k, v = (torch.randn(B, N, H * d, device=dev).to(torch.bfloat16) for _ in range(3))
@@ -50,6 +54,8 @@ def main():
             out.append(rec)
         # torch SDPA (library flash attention) for context only
         q4, k4, v4 = (t.view(B, N, H, d).transpose(1, 2) for t in (q, k, v))
+        if no_sdpa:
+            continue
         try:
             med, best = time_call(lambda: torch.nn.functional.scaled_dot_product_attention(q4, k4, v4))
             print(json.dumps(dict(shape=name, impl="torch_sdpa", ms_median=round(med, 4), tflops_median=round(flops / med / 1e9, 1))), flush=True)

@@ -11,11 +11,10 @@ IEF_TC_VERSION=2 IEF_TC_SPLITKV=0 run tc_v2_pair "tcgen05 or fp16 or row_sources
 IEF_TC_SPLITKV=1 run tc_v3_split "tcgen05 or fp16 or row_sources or masactrl or lazy or strided"
 IEF_TC_SPLITKV=2 run tc_v3_hybrid "tcgen05 or fp16 or row_sources or masactrl or lazy or strided"
 IEF_TC_SPLITKV=0 run tc_v3_pair "tcgen05 or fp16 or row_sources or masactrl or lazy or strided"
-IEF_TC_VERSION=2 IEF_TC_SPLITKV=1 run tc_v2_split "tcgen05 or fp16 or row_sources or masactrl or lazy or strided"
 IEF_TC_VERSION=1 run tc_v1 "tcgen05 or fp16 or row_sources or masactrl or lazy or strided"
 IEF_TC3_NO_SUM_MMA=1 run tc_v3_no_summma "tcgen05 or fp16 or row_sources or masactrl or lazy or strided"
 IEF_TC3_SKIPMAX=2 run tc_v3_skip_everywhere "tcgen05 or fp16 or row_sources or masactrl or lazy or strided"
-IEF_TC3_SKIPMAX=0 run tc_v3_no_skip "tcgen05 or fp16 or row_sources or masactrl or lazy or strided"
+IEF_TC3_NOMAX=0 run tc_v3_exact_only "tcgen05 or fp16 or row_sources or masactrl or lazy or strided"
 run cross "cross_attention"
 IEF_CROSS_TC=0 run cross_mma_only "cross_attention"
 run masked "key_bias or mask_blend"
@@ -30,5 +29,6 @@ IEF_TC_VERSION=2 fuzz v2
 IEF_TC_SPLITKV=0 fuzz v3_pair
 IEF_TC_SPLITKV=1 fuzz v3_split
 IEF_TC3_SKIPMAX=2 fuzz skip_everywhere
+IEF_TC3_NOMAX=0 fuzz exact_only
 IEF_PROBS_VIA_LSE=0 fuzz probs_two_sweep
 IEF_TC3_NO_SUM_MMA=1 fuzz no_summma

@@ -33,6 +33,9 @@ for j in range(4, min(nt, 12)):
     for s_ in range(2):
         r = [int(x) for x in sm[s_, j]]
         period = r[0] - int(sm[s_, j - 1, 0])
+        if int(s2[s_, j, 0]) == 0:   # unshifted loop (MAXMODE 2): no maximum / exchange / decision sub-phases
+            print(f"  t{s_} j={j:2d} | {r[0] - t0:7d} | {r[1] - r[0]:6d} {r[2] - r[1]:5d} [   -      -      - {r[6] - r[2]:6d}] {r[7] - r[6]:8d} {r[3] - r[7]:10d} {r[4] - r[3]:8d} {r[5] - r[4]:7d} | {period}")
+            continue
         print(f"  t{s_} j={j:2d} | {r[0] - t0:7d} | {r[1] - r[0]:6d} {r[2] - r[1]:5d} [{int(s2[s_, j, 0]) - r[2]:4d} {int(s2[s_, j, 1] - s2[s_, j, 0]):6d} {int(s2[s_, j, 2] - s2[s_, j, 1]):6d} {r[6] - int(s2[s_, j, 2]):6d}] {r[7] - r[6]:8d} {r[3] - r[7]:10d} {r[4] - r[3]:8d} {r[5] - r[4]:7d} | {period}")
 tot = int(sm[0, nt - 1, 5] - sm[0, 0, 0])
 print(f"total cycles for {nt} tiles (stream 0): {tot} -> {tot / nt:.0f} per tile")
