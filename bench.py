@@ -12,9 +12,11 @@ attention inside it and the step update are this repo's kernels — the rest sta
   python bench.py --impl reference ...                     the CPU arm: the reference's materialise-edit-multiply arithmetic
                                                            (oracle port) on the host cores, bounded sample per step
 
-`value`  : edits/s with the inputs (inverted-image latent + prompt embeddings) already resident in HBM.
-`e2e`    : the same through the public driver with HOST buffers: pinned host -> device copy of the step's inputs and a
-           device -> host read of the edited latents inside the timed region.
+Both numbers go through the public, reference-named API (class MasaCtrlEdit below = the call sequence of masactrl/edit_real.py).
+`value`  : edits/s with the image's VAE latent already resident in HBM.
+`e2e`    : the same from a HOST uint8 image: image2latent (host -> device copy + VAE encode), inversion, controlled edit, VAE decode
+           and the two uint8 result images read back to the host inside the timed region.
+`gpu_reference_baseline`: the reference's formulation (fp32, materialised probabilities, torch eager) for one whole edit on the same B200.
 `roofline`: the dominant kernel (tcgen05 controlled self-attention at 64x64 latents: B=4,H=8,N=4096,d=40) timed with CUDA
            events on the launching stream inside the timed region; algorithmic FLOPs 4*B*H*N*N*d per launch.
 """
@@ -89,6 +91,17 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ workload
+def workload_config(ddim_steps, cfg_name):
+    """The `config` object both arms print (identical by construction): the workload, not how an arm runs it."""
+    return {"workload": f"configs[1]: MasaCtrl mutual self-attention (start step {START_STEP}, layer {START_LAYER}), SD-1.5 512^2, "
+                        f"{ddim_steps} DDIM inversion forwards (B=1) + {ddim_steps} edit forwards (B=4 = src+tgt x CFG), guidance {GUIDANCE}, "
+                        f"one synthetic 512x512 image per step",
+            "unet": (f"random-init stand-in with SD-1.5's full architecture and cost ({cfg_name}, 860 M parameters)" if cfg_name != "tiny" else
+                     "DEBUG tiny stand-in UNet (not the headline workload)") + "; text encoder and VAE are token stand-ins (no weights offline)",
+            "images_per_gpu_per_step": 1,
+            "l2": "per-forward working set (1.7 GB of weights + activations) exceeds the 126 MB L2; no explicit flush"}
+
+
 def build_pipeline(config_name, device, dtype):
     import torch
     from image_editing_framework_b200.standin import make_pipeline, sd15_config, tiny_config
@@ -130,11 +143,82 @@ class KernelTimer:
         return (sum(ms) / len(ms), len(ms)) if ms else (None, 0)
 
 
+class MasaCtrlEdit:
+    """One complete edit through the PUBLIC, reference-named API — the call sequence of masactrl/edit_real.py:125-139:
+
+        latent        = ddim_inversion().image2latent(pipe, image, device, dtype)
+        trajectory, _ = ddim_inversion().ddim_inversion_loop(pipe, latent, source_prompt)        # 50 B=1 forwards
+        regiter_attention_editor_diffusers(pipe, MutualSelfAttentionControl(4, 10))
+        images, _     = MasaCtrl(pipe, 50)(source_prompt + target_prompt, latents=cat([x_T, x_T]), guidance_scale=7.5)   # 50 B=4 forwards
+
+    Objects are kept across edits (editor.reset() in between), as a server would, so that graphs=True replays instead of re-capturing.
+    During the inversion a do-nothing masactrl.AttentionBase() is registered: the reference inverts on the un-hooked UNet (library
+    attention); registering the base editor routes those 32 attention layers per forward through this repo's kernels as well."""
+
+    def __init__(self, pipe, ddim_steps, graphs):
+        from image_editing_framework_b200 import masactrl
+        from image_editing_framework_b200.ddim import ddim_inversion
+        self.pipe, self.steps, self.m = pipe, ddim_steps, masactrl
+        self.inv = ddim_inversion()
+        self.inv.graphs = graphs
+        self.plain = masactrl.AttentionBase()
+        self.editor = masactrl.MutualSelfAttentionControl(START_STEP, START_LAYER, total_steps=ddim_steps)
+        self.sampler = masactrl.MasaCtrl(pipe, ddim_steps, graphs=graphs)
+
+    def from_latent(self, latent):
+        m, pipe = self.m, self.pipe
+        pipe.scheduler.set_timesteps(self.steps)
+        self.plain.reset()
+        m.regiter_attention_editor_diffusers(pipe, self.plain)
+        try:
+            trajectory, _ = self.inv.ddim_inversion_loop(pipe, latent, PROMPTS[:1])
+        finally:
+            m.unregister_attention_control(pipe, self.plain)
+        self.editor.reset()
+        m.regiter_attention_editor_diffusers(pipe, self.editor)
+        try:
+            x_t = trajectory[-1]
+            images, _ = self.sampler(PROMPTS, latents=__import__("torch").cat([x_t, x_t]), guidance_scale=GUIDANCE, num_inference_steps=self.steps)
+        finally:
+            m.unregister_attention_control(pipe, self.editor)
+        return images                      # uint8 [2, 512, 512, 3] on the host (inversion reconstruction, edit)
+
+    def from_image(self, image_u8, device, dtype):
+        return self.from_latent(self.inv.image2latent(self.pipe, image_u8, device, dtype))
+
+    def replayed_launches(self):
+        runners = list(self.pipe.unet.__dict__.get("_ief_inversion_runners", {}).values())
+        if getattr(self.sampler, "_runner", None) is not None:
+            runners.append(self.sampler._runner)
+        return sum(r.replayed_launches for r in runners)
+
+
+def dominant_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE call of the dominant kernel, read from the committed ncu summary that
+    profiles/dominant_kernel.json points at (so the figure cannot outlive the capture it came from). None when there is none."""
+    try:
+        man = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel.json")))
+        text = open(os.path.join(ROOT, "profiles", man["summary"])).read()
+        total, sections = 0.0, text.split("\n== ")[1:]
+        for sec in sections:
+            if not any(sec.rstrip().splitlines()[0].endswith(f"id={i}") for i in man["launch_ids_of_one_call"]):
+                continue
+            for line in sec.splitlines():
+                f = line.split()
+                if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    total += float(f[1]) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[f[2]]
+        return {"bytes": total, "source": "profiles/" + man["summary"]}
+    except Exception as e:   # noqa: BLE001 - a missing / unparsable profile just means "not captured"
+        return {"bytes": None, "source": f"unavailable: {e}"}
+
+
 def run_ours(args):
+    import contextlib as _ctx
+    import io
+    import numpy as np
     import torch
     import torch.distributed as dist
-    from image_editing_framework_b200 import _cabi, ops, masactrl
-    from image_editing_framework_b200.editing import encode_prompts
+    from image_editing_framework_b200 import _cabi, ops
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -145,102 +229,17 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     _cabi.check("ief_check_device", _cabi.lib().ief_check_device())
-    torch.backends.cuda.matmul.allow_tf32 = True
     pipe, cfg = build_pipeline(args.config, dev, torch.bfloat16)
     hw = cfg.sample_size
-    regs = (masactrl.regiter_attention_editor_diffusers, masactrl.unregister_attention_control)
-    # inversion runs through the same fused closures with a do-nothing editor registered (plain attention, B=1)
-    plain = masactrl.AttentionBase()
-    context = encode_prompts(pipe, PROMPTS)                      # [uncond, uncond, cond_src, cond_tgt] x 77 x 768, bf16
-    gen = torch.Generator().manual_seed(1234 + rank)
-    host_latent = (torch.randn(1, 4, hw, hw, generator=gen) * 0.18215 * 5).to(torch.bfloat16).pin_memory()  # "VAE-encoded synthetic image"
-    host_context = context.cpu().pin_memory()
-    host_out = torch.empty(2, 4, hw, hw, dtype=torch.bfloat16).pin_memory()
-    dev_latent = host_latent.to(dev)
-
-    import io
-    import contextlib as _ctx
-
-    def quiet_ctx():  # the reference's editor prints its step/layer lists on construction
-        return _ctx.redirect_stdout(io.StringIO())
-
     use_graphs = not args.no_graphs
     if not args.no_channels_last:
         pipe.unet.to(memory_format=torch.channels_last)
-    t_dev = {}   # timestep -> 0-dim device tensor (no per-step host->device copy)
-
-    def tstep(t):
-        if t not in t_dev:
-            t_dev[t] = torch.tensor(t, dtype=torch.int64, device=dev)
-        return t_dev[t]
-
-    def unet_fwd(x, t, ctx):
-        return pipe.unet(x, t, encoder_hidden_states=ctx).sample
-
-    graphs = {}
-    if use_graphs:
-        from image_editing_framework_b200.graphs import GraphedCall
-        # three control patterns -> three graphs: inversion (B=1, plain), edit before start_step (B=4, plain),
-        # edit from start_step on (B=4, MasaCtrl layers controlled). Controller counters are ticked by hand on replay.
-        regs[0](pipe, plain)
-        graphs["inv"] = GraphedCall(unet_fwd, [dev_latent, tstep(1), context[2:3].contiguous()], launch_counter=_cabi.launch_count)
-        x4 = torch.cat([dev_latent] * 4)
-        graphs["edit_plain"] = GraphedCall(unet_fwd, [x4, tstep(1), context], launch_counter=_cabi.launch_count)
-        regs[1](pipe, plain)
-        with quiet_ctx():
-            cap_editor = masactrl.MutualSelfAttentionControl(START_STEP, START_LAYER, total_steps=args.ddim_steps)
-        regs[0](pipe, cap_editor)
-        cap_editor.cur_step = START_STEP
-
-        def fwd_ctrl(x, t, ctx):
-            cap_editor.cur_step, cap_editor.cur_att_layer = START_STEP, 0   # every capture/warm-up pass sees a controlled step
-            return unet_fwd(x, t, ctx)
-        graphs["edit_ctrl"] = GraphedCall(fwd_ctrl, [x4, tstep(1), context], launch_counter=_cabi.launch_count)
-        regs[1](pipe, cap_editor)
-
-    def _edit(lat, ctx, eager=False):
-        from image_editing_framework_b200.ddim import FusedDDIM
-        pipe.scheduler.set_timesteps(args.ddim_steps)
-        fused = FusedDDIM(pipe.scheduler)
-        ts = pipe.scheduler.timesteps.tolist()
-        cond_src = ctx[2:3]
-        with torch.no_grad():
-            if use_graphs and not eager:
-                for t in reversed(ts):
-                    eps = graphs["inv"](lat, tstep(t), cond_src)
-                    lat = fused.reverse_step(eps, t, lat)
-                latents = torch.cat([lat, lat])
-                for i, t in enumerate(ts):
-                    g = graphs["edit_ctrl"] if i >= START_STEP else graphs["edit_plain"]
-                    eps = g(torch.cat([latents] * 2), tstep(t), ctx)
-                    latents = fused.step(eps, t, latents, GUIDANCE)
-                return latents
-            regs[0](pipe, plain)
-            for t in reversed(ts):
-                eps = unet_fwd(lat, tstep(t), cond_src)
-                lat = fused.reverse_step(eps, t, lat)
-            regs[1](pipe, plain)
-            editor = masactrl.MutualSelfAttentionControl(START_STEP, START_LAYER, total_steps=args.ddim_steps)
-            regs[0](pipe, editor)
-            latents = torch.cat([lat, lat])
-            for i, t in enumerate(ts):
-                # NVTX range for `ncu --nvtx --nvtx-include "edit_ctrl/"`: one MasaCtrl-controlled B=4 forward + step update
-                torch.cuda.nvtx.range_push("edit_ctrl" if i >= START_STEP else "edit_plain")
-                eps = unet_fwd(torch.cat([latents] * 2), tstep(t), ctx)
-                latents = fused.step(eps, t, latents, GUIDANCE)
-                torch.cuda.nvtx.range_pop()
-            regs[1](pipe, editor)
-        return latents
-
-    def edit_from_host():
-        lat = host_latent.to(dev, non_blocking=True)
-        ctx = host_context.to(dev, non_blocking=True)
-        out = _edit(lat, ctx)
-        host_out.copy_(out, non_blocking=True)
-        torch.cuda.current_stream().synchronize()   # the caller reads the edited latents on the host
-        return host_out
-
-    quiet = quiet_ctx()
+    rng = np.random.default_rng(1234 + rank)
+    host_image = rng.integers(0, 256, size=(hw * 8, hw * 8, 3), dtype=np.uint8)        # the synthetic 512x512 image, on the host
+    with torch.no_grad():
+        dev_latent = MasaCtrlEdit(pipe, args.ddim_steps, False).inv.image2latent(pipe, host_image, dev, torch.bfloat16)
+    edit = MasaCtrlEdit(pipe, args.ddim_steps, use_graphs)
+    eager = MasaCtrlEdit(pipe, args.ddim_steps, False) if use_graphs else edit
 
     def barrier():
         torch.cuda.synchronize()
@@ -248,14 +247,13 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    def timed(fn, k):
+    def timed(fn, k, runner_owner):
         barrier()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0 = _cabi.launch_count()
-        timed.replayed_before = sum(g.captured_launches * g.replays for g in graphs.values())
+        l0, r0 = _cabi.launch_count(), runner_owner.replayed_launches()
         s.record()
         for _ in range(k):
-            fn()
+            out = fn()
         e.record()
         barrier()
         ms = s.elapsed_time(e)
@@ -263,29 +261,27 @@ def run_ours(args):
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = t.item()
-        replayed = sum(g.captured_launches * g.replays for g in graphs.values())
-        return ms, _cabi.launch_count() - l0 + replayed - timed.replayed_before
-
-    timed.replayed_before = 0
+        assert out.dtype == np.uint8 and out.shape == (2, hw * 8, hw * 8, 3), (out.dtype, out.shape)
+        return ms, _cabi.launch_count() - l0 + runner_owner.replayed_launches() - r0
 
     dom_shape = (4, 8, hw * hw, cfg.block_out_channels[0] // cfg.num_heads[0])
-    with quiet, KernelTimer(ops, dom_shape) as kt:
+    with _ctx.redirect_stdout(io.StringIO()), KernelTimer(ops, dom_shape) as kt:   # the reference's editor prints its step / layer lists
         for _ in range(args.warmup):
-            _edit(dev_latent, context)
+            edit.from_latent(dev_latent)
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
         kt.on = not use_graphs
-        ms_res, launches = timed(lambda: _edit(dev_latent, context), args.steps)
+        ms_res, launches = timed(lambda: edit.from_latent(dev_latent), args.steps, edit)
         kt.on = False
-        ms_e2e, _ = timed(edit_from_host, args.steps)
+        ms_e2e, _ = timed(lambda: edit.from_image(host_image, dev, torch.bfloat16), args.steps, edit)
         ms_eager = None
         if use_graphs:
             # per-launch CUDA events cannot be read from inside a replayed graph: the dominant kernel is timed in situ in an
             # eager pass of the same edits (same launches, same neighbours), which also reports what eager mode costs
-            _edit(dev_latent, context, eager=True)
+            eager.from_latent(dev_latent)
             kt.on = True
-            ms_eager, _ = timed(lambda: _edit(dev_latent, context, eager=True), args.steps)
+            ms_eager, _ = timed(lambda: eager.from_latent(dev_latent), args.steps, eager)
             kt.on = False
         clocks = sampler.stop() if rank == 0 else None
     kern_ms, kern_n = kt.mean_ms()
@@ -299,90 +295,150 @@ def run_ours(args):
     flops = 4.0 * B * H * N * N * d
     achieved = flops / (kern_ms * 1e-3) / 1e12 if kern_ms else None
     peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])   # timed inside a long step -> sustained figure
+    traffic = dominant_traffic()
     line = {
         "metric": METRIC, "value": round(world * args.steps / (ms_res * 1e-3), 4), "unit": "edits/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms_res / args.steps, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"configs[1]: MasaCtrl mutual self-attention (start step {START_STEP}, layer {START_LAYER}), SD-1.5 512^2, "
-                               f"{args.ddim_steps} DDIM inversion forwards (B=1) + {args.ddim_steps} edit forwards (B=4), guidance {GUIDANCE}",
-                   "unet": f"random-init stand-in with SD-1.5's full architecture ({cfg.name}); attention + step update = libief_b200 kernels, rest PyTorch eager bf16",
-                   "cuda_graphs": use_graphs, "channels_last": not args.no_channels_last,
-                   "eager_ms_per_step": round(ms_eager / args.steps, 2) if ms_eager else None,
-                   "images_per_gpu_per_step": 1, "parallelism": f"image-sharded x{world}, no collective on the hot path",
-                   "l2": "per-forward working set (1.7 GB of weights + activations) exceeds the 126 MB L2; no explicit flush"},
+        "config": workload_config(args.ddim_steps, cfg.name),
+        "impl_config": {"api": "ddim_inversion().ddim_inversion_loop + regiter_attention_editor_diffusers + MasaCtrl(pipe, 50, graphs=True)(...) "
+                               "(the reference-named classes, call sequence of masactrl/edit_real.py:125-139); uint8 images returned on the host",
+                        "attention + step update": "libief_b200 kernels; rest of the UNet PyTorch eager bf16",
+                        "cuda_graphs": use_graphs, "channels_last": not args.no_channels_last,
+                        "eager_ms_per_step": round(ms_eager / args.steps, 2) if ms_eager else None,
+                        "parallelism": f"image-sharded x{world}, no collective on the hot path"},
         "clocks": clocks,
         "e2e": {"value": round(world * args.steps / (ms_e2e * 1e-3), 4), "unit": "edits/s",
-                "h2d_bytes_per_step": host_latent.numel() * 2 + host_context.numel() * 2, "d2h_bytes_per_step": host_out.numel() * 2,
-                "note": "pinned-host latents + text context in, edited latents out and a stream sync every step; the copies are well under "
-                        "0.1 ms of a ~0.9 s step, so e2e tracks value within run-to-run noise (about 1 %)"},
+                "h2d_bytes_per_step": int(host_image.size) * 2 + 3 * 77 * 8, "d2h_bytes_per_step": 2 * int(host_image.size),
+                "note": "host uint8 image -> image2latent (bf16 pixels copied to the device, VAE stand-in) -> inversion -> controlled edit -> "
+                        "VAE decode -> two uint8 images read back to the host (a blocking copy) every step; prompts tokenised on the host"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "kernel": "tcgen05 gen-3b controlled self-attention (attn_tc3_kernel, row sums on the tensor pipe; one call = full waves as 256-row pair CTAs + remainder as split-KV CTAs, bf16) B=4 H=8 N=4096 d=40", "timed_in": "eager pass of the same edits" if use_graphs else "the timed region",
+        "roofline": {"bound": "tensor", "kernel": "attn_tc3_kernel (tcgen05 controlled self-attention, unshifted-softmax generation; one call = full waves "
+                                                  "as 256-row pair CTAs + remainder as split-KV CTAs, bf16) B=4 H=8 N=4096 d=40",
+                     "timed_in": "eager pass of the same edits" if use_graphs else "the timed region",
                      "achieved": round(achieved, 1) if achieved else None, "peak": peak, "peak_source": f"{pk_src} bf16_tflops_sustained",
                      "unit": "TFLOP/s", "frac": round(achieved / peak, 4) if achieved else None,
                      "frac_of_burst_peak": round(achieved / pk["bf16_tflops"], 4) if achieved else None,
                      "launches_timed": kern_n, "mean_launch_ms": round(kern_ms, 4) if kern_ms else None,
-                     "algorithmic_flops_per_launch": flops, "traffic": TRAFFIC_BYTES_PER_LAUNCH},
+                     "algorithmic_flops_per_launch": flops, "traffic": traffic["bytes"], "traffic_source": traffic["source"]},
     }
     if not args.no_cpu_baseline and world == 1:
-        line["cpu_baseline"] = cpu_sample(args)
+        del edit, eager
+        torch.cuda.empty_cache()
+        line["gpu_reference_baseline"] = gpu_reference_sample(args, dev)
+        line["cpu_baseline"] = cpu_sample(args)["baseline"]
     emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from profiles/ (one ncu --set full capture); None until captured
-TRAFFIC_BYTES_PER_LAUNCH = 26.62e6  # profiles/r01_attn_tc3_summma_sd15_64_ncu_full.txt: dram read 20.10 MB (pair launch) + 6.53 MB (split-KV launch), writes < 1 KB (O stays in L2)
+# ------------------------------------------------------------------------------------------------ reference-formulation arms
+_REF_PIPE = {}
 
 
-# ------------------------------------------------------------------------------------------------ CPU arm
-_CPU_PIPE = {}
+def reference_edit(pipe, args, device, ddim_steps):
+    """One edit in the REFERENCE's formulation: fp32, torch eager, materialised probabilities — `sim` and `attn` computed on every
+    layer and the controlled layers recomputed per CFG half (masactrl/model/register.py:35-44, attention_control.py:37-68), i.e.
+    the oracle port driven through the same closures (oracle/cpu_ops.py with reference_work on). Returns the final latents."""
+    import contextlib
+    import io
+    import torch
+    from oracle import cpu_ops
+    from image_editing_framework_b200 import masactrl
+    from image_editing_framework_b200.editing import encode_prompts, masactrl_edit
+    from image_editing_framework_b200.ddim import ddim_inversion
+    hw = pipe.unet.config.sample_size
+    lat = (torch.randn(1, 4, hw, hw, generator=torch.Generator().manual_seed(1)) * 0.9).to(device)
+    with cpu_ops.patched(reference_work=True), torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+        pipe.scheduler.set_timesteps(ddim_steps)
+        traj, _ = ddim_inversion().ddim_inversion_loop(pipe, lat, PROMPTS[:1])       # un-hooked UNet, as the reference inverts
+        ed = masactrl.MutualSelfAttentionControl(START_STEP, START_LAYER, total_steps=ddim_steps)
+        masactrl.regiter_attention_editor_diffusers(pipe, ed)
+        try:
+            out = masactrl_edit(pipe, PROMPTS, torch.cat([traj[-1]] * 2), ddim_steps, GUIDANCE, context=encode_prompts(pipe, PROMPTS))
+        finally:
+            masactrl.unregister_attention_control(pipe, ed)
+    return out
 
 
-def cpu_sample(args, reps=1):
-    """Bounded sample of the same workload on the host cores: the reference's arithmetic (materialised fp32 probabilities,
-    oracle port) driven through the same closures. Sample = one inversion forward (B=1) + one controlled edit forward
-    (B=4, step >= 4) of the full-cost UNet; an edit is 50 of each, so edits/s = 1 / (50 * (t_B1 + t_B4))."""
+def gpu_reference_sample(args, dev):
+    """The fair GPU baseline: the reference formulation, fp32, torch eager, on the SAME B200. One complete
+    edit at the full step count, timed with a device synchronisation on both sides."""
+    import torch
+    from image_editing_framework_b200.standin.unet import AttnProcessor
+    tf32, sdpa = torch.backends.cuda.matmul.allow_tf32, AttnProcessor.use_sdpa
+    torch.backends.cuda.matmul.allow_tf32 = False       # torch's default, what the reference's scripts run with
+    AttnProcessor.use_sdpa = True                        # the un-hooked inversion runs diffusers' default processor (library SDPA)
+    pipe = None
+    try:
+        pipe, cfg = build_pipeline(args.config, dev, torch.float32)
+        reference_edit(pipe, args, dev, 2)               # warm-up: allocator, cuDNN autotune
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        reference_edit(pipe, args, dev, args.ddim_steps)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        peak_gb = torch.cuda.max_memory_allocated() / 2 ** 30
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, AttnProcessor.use_sdpa = tf32, sdpa
+        del pipe
+        torch.cuda.empty_cache()
+    return {"value": round(1.0 / dt, 5), "unit": "edits/s", "ms_per_edit": round(dt * 1e3, 1), "kind": "port",
+            "what": "reference formulation (fp32, materialised sim + attn on every layer, controlled layers recomputed per CFG half), torch eager, "
+                    f"same B200, one full {args.ddim_steps}+{args.ddim_steps}-forward edit from a device-resident latent to final latents",
+            "peak_memory_gib": round(peak_gb, 1)}
+
+
+def cpu_sample(args):
+    """Bounded sample of the same workload on the host cores, in the reference's formulation (see reference_edit): a COMPLETE edit
+    at `--cpu-ddim-steps` (default 1) inversion + edit forwards of the full-cost UNet, plus one controlled edit forward (step >=
+    start_step) — at one step no layer is controlled yet, so the controlled forward is timed separately. edits/s is extrapolated to
+    the full step count: t = steps * t_inversion_fwd + start_step * t_plain_fwd + (steps - start_step) * t_controlled_fwd."""
+    import contextlib
+    import io
     import torch
     from oracle import cpu_ops
     from image_editing_framework_b200 import masactrl
     from image_editing_framework_b200.editing import encode_prompts
-    import io
-    import contextlib
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    if args.config not in _CPU_PIPE:
-        _CPU_PIPE[args.config] = build_pipeline(args.config, torch.device("cpu"), torch.float32)
-    pipe, cfg = _CPU_PIPE[args.config]
+    if args.config not in _REF_PIPE:
+        _REF_PIPE[args.config] = build_pipeline(args.config, torch.device("cpu"), torch.float32)
+    pipe, cfg = _REF_PIPE[args.config]
     hw = cfg.sample_size
     context = encode_prompts(pipe, PROMPTS)
     lat = torch.randn(1, 4, hw, hw, generator=torch.Generator().manual_seed(1))
     pipe.scheduler.set_timesteps(args.ddim_steps)
     t_mid = pipe.scheduler.timesteps.tolist()[len(pipe.scheduler.timesteps) // 2]
-    times = []
-    with cpu_ops.patched(), torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
-        for _ in range(reps):
-            plain = masactrl.AttentionBase()
-            masactrl.regiter_attention_editor_diffusers(pipe, plain)
-            t0 = time.perf_counter()
-            pipe.unet(lat, t_mid, encoder_hidden_states=context[2:3])
-            t1 = time.perf_counter()
-            masactrl.unregister_attention_control(pipe, plain)
-            ed = masactrl.MutualSelfAttentionControl(START_STEP, START_LAYER, total_steps=args.ddim_steps)
-            masactrl.regiter_attention_editor_diffusers(pipe, ed)
+    wall0 = time.perf_counter()
+    with cpu_ops.patched(reference_work=True), torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+        t0 = time.perf_counter()
+        pipe.unet(lat, t_mid, encoder_hidden_states=context[2:3])                   # inversion forward: un-hooked UNet, B=1
+        t_b1 = time.perf_counter() - t0
+        ed = masactrl.MutualSelfAttentionControl(START_STEP, START_LAYER, total_steps=args.ddim_steps)
+        masactrl.regiter_attention_editor_diffusers(pipe, ed)
+        try:
             ed.cur_step = max(START_STEP, args.ddim_steps // 2)
-            t2 = time.perf_counter()
-            pipe.unet(torch.cat([lat] * 4), t_mid, encoder_hidden_states=context)
-            t3 = time.perf_counter()
+            t0 = time.perf_counter()
+            pipe.unet(torch.cat([lat] * 4), t_mid, encoder_hidden_states=context)   # controlled edit forward, B=4
+            t_ctrl = time.perf_counter() - t0
+        finally:
             masactrl.unregister_attention_control(pipe, ed)
-            times.append((t1 - t0, t3 - t2))
-    t_b1 = min(t[0] for t in times)
-    t_b4 = min(t[1] for t in times)
-    return {"value": round(1.0 / (args.ddim_steps * (t_b1 + t_b4)), 6), "unit": "edits/s", "cores": cores, "kind": "port",
-            "sample": f"1 inversion UNet forward (B=1, {t_b1:.2f} s) + 1 MasaCtrl-controlled edit forward (B=4, {t_b4:.2f} s), fp32, torch on {cores} threads; "
-                      f"extrapolated x{args.ddim_steps} each"}
+    # a plain (step < start_step) edit forward does the controlled forward's work minus the six recomputed layers: bounded above by it
+    n = args.ddim_steps
+    t_edit = n * t_b1 + n * t_ctrl
+    wall = time.perf_counter() - wall0
+    base = {"value": round(1.0 / t_edit, 6), "unit": "edits/s", "cores": cores, "kind": "port",
+            "sample": f"1 inversion UNet forward (B=1, {t_b1:.2f} s) + 1 MasaCtrl-controlled edit forward (B=4, {t_ctrl:.2f} s) of the full-cost UNet in the "
+                      f"reference formulation (fp32, sim + attn materialised on every layer, controlled layers recomputed), torch on {cores} threads; "
+                      f"edits/s extrapolated as 1 / ({n} x B=1 + {n} x B=4), the first {START_STEP} un-controlled edit forwards charged at the controlled cost",
+            "extrapolated": True}
+    return {"baseline": base, "wall_s": wall}
 
 
 def run_reference(args):
+    """`--impl reference`: the CPU arm. A "step" here is ONE bounded sample (cpu_sample) of the workload, and ms_per_step is its
+    real wall time; `value` is the metric extrapolated from the sample as cpu_baseline.sample says."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -392,15 +448,20 @@ def run_reference(args):
         s = cpu_sample(args)
         if i >= args.warmup:
             samples.append(s)
-        if time.perf_counter() - t0 > 240 and len(samples) >= 1:   # keep the whole arm within a few minutes
+        if time.perf_counter() - t0 > 200 and len(samples) >= 1:   # keep the whole arm within a few minutes
             break
-    v = statistics.median(s["value"] for s in samples)
-    base = dict(samples[-1])
+    v = statistics.median(s["baseline"]["value"] for s in samples)
+    base = dict(samples[-1]["baseline"])
     base["value"] = v
+    cfgname = "sd15" if args.config == "sd15" else "tiny"
+    from image_editing_framework_b200.standin import sd15_config, tiny_config
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "edits/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
-            "steps": len(samples), "warmup": args.warmup, "ms_per_step": round(1e3 / v, 1), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"configs[1]: MasaCtrl mutual self-attention, SD-1.5 512^2, {args.ddim_steps}+{args.ddim_steps} UNet forwards; bounded CPU sample per step"},
+            "steps": len(samples), "warmup": min(args.warmup, max(0, args.warmup + args.steps - len(samples))),
+            "ms_per_step": round(1e3 * statistics.median(s["wall_s"] for s in samples), 1),
+            "ms_per_step_is": "wall time of one bounded sample (2 UNet forwards), not of one edit; ms per extrapolated edit = 1000 / value",
+            "ms_per_edit_extrapolated": round(1e3 / v, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.ddim_steps, (sd15_config() if cfgname == "sd15" else tiny_config()).name),
             "cpu_baseline": base, "e2e": {"value": v, "unit": "edits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 

@@ -101,7 +101,7 @@ class UmmaProbeParams(C.Structure):
 # every symbol include/ief_b200.h declares; tests check the .so exports each one
 EXPORTS = (
     "ief_attn_fwd", "ief_attn_workspace_bytes", "ief_cross_attn_edit_fwd", "ief_cross_attn_bwd", "ief_store_accumulate", "ief_local_blend", "ief_mask_blend", "ief_cfg_ddim_step",
-    "ief_umma_probe", "ief_abi_version", "ief_last_error", "ief_launch_count", "ief_last_attn_impl", "ief_check_device",
+    "ief_umma_probe", "ief_abi_version", "ief_last_error", "ief_launch_count", "ief_last_attn_impl", "ief_last_cross_impl", "ief_check_device",
 )
 
 _lib = None
@@ -152,6 +152,7 @@ def lib() -> C.CDLL:
         L.ief_abi_version.restype = C.c_int
         L.ief_last_error.restype = C.c_char_p
         L.ief_last_attn_impl.restype = C.c_char_p
+        L.ief_last_cross_impl.restype = C.c_char_p
         L.ief_launch_count.restype = C.c_int64
         L.ief_check_device.restype = C.c_int
         L.ief_attn_fwd.argtypes = [C.POINTER(AttnParams), C.c_void_p]
@@ -198,3 +199,7 @@ def launch_count() -> int:
 
 def last_attn_impl() -> str:
     return lib().ief_last_attn_impl().decode()
+
+
+def last_cross_impl() -> str:
+    return lib().ief_last_cross_impl().decode()

@@ -127,14 +127,29 @@ __device__ __forceinline__ void scale_chunk_mix(uint32_t (&s)[32], float2 c2, fl
   }
 }
 
+// Row sums in registers (head_dim > 48: no accumulator columns left for the row-sum MMA). bf16: the sum is taken over the SAME 16-bit
+// values the PV MMA multiplies — the fp32 exponentials cut to their upper halves (2 LOP3 + 1 PRMT instead of 1 F2FP per pair) — so that
+// O = sum(p v) / sum(p) is a ratio of consistently rounded terms. Summing the unrounded fp32 p against rounded P in the numerator costs
+// up to 2^-9 |v| on peaked rows whenever the dominant p is not exactly 1 (stale lazy maximum, or the unshifted loop, where it never is):
+// 0.031 observed at |v| = 5 (tools/diag/overflow_case.py). fp16 keeps round-to-nearest packing (11-bit P: a quarter of that error).
+#ifndef IEF_TC3_CONSISTENT_SUM
+#define IEF_TC3_CONSISTENT_SUM 1
+#endif
 template <typename E, int EVERY>
 __device__ __forceinline__ void exp_pack_chunk_mix(const uint32_t (&s)[32], uint32_t (&u)[16], float2& acc0, float2& acc1) {
+  constexpr bool cut = IEF_TC3_CONSISTENT_SUM && sizeof(typename E::T) == 2 && E::kIsBf16;
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     float2 x = make_float2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1]));
     if (!emul_pair<EVERY>(i)) { x.x = ief_exp2(x.x); x.y = ief_exp2(x.y); }
+    if constexpr (cut) {
+      const uint32_t lo = __float_as_uint(x.x) & 0xffff0000u, hi = __float_as_uint(x.y) & 0xffff0000u;
+      x = make_float2(__uint_as_float(lo), __uint_as_float(hi));
+      u[i] = __byte_perm(lo, hi, 0x7632);
+    } else {
+      u[i] = E::pack(x.x, x.y);
+    }
     if (i & 1) acc1 = fadd2(acc1, x); else acc0 = fadd2(acc0, x);
-    u[i] = E::pack(x.x, x.y);
   }
 }
 

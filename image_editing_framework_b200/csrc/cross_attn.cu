@@ -291,6 +291,9 @@ int launch_flavour(const CrossArgs& a, int flavour, dim3 grid, cudaStream_t st) 
 
 }  // namespace
 
+namespace { thread_local const char* g_last_cross_impl = "none"; }
+extern "C" const char* ief_last_cross_impl(void) { return g_last_cross_impl; }
+
 extern "C" int ief_cross_attn_edit_fwd(const ief_cross_params* p, void* stream) {
   IEF_REQUIRE(p != nullptr, IEF_ERR_INVALID, "ief_cross_attn_edit_fwd: null params");
   IEF_REQUIRE(p->q.ptr && p->k.ptr && p->v.ptr && p->o.ptr, IEF_ERR_INVALID, "ief_cross_attn_edit_fwd: null tensor pointer");
@@ -335,7 +338,11 @@ extern "C" int ief_cross_attn_edit_fwd(const ief_cross_params* p, void* stream) 
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   // un-edited rows without a map output: the tcgen05 kernel (cross_tc.cu), a row per thread instead of a row per quad
-  if (flavour == kPlain && p->probs_out == nullptr && ief_cross_tc_supported(p)) return ief_cross_tc_launch(p, st);
+  if (flavour == kPlain && p->probs_out == nullptr && ief_cross_tc_supported(p)) {
+    g_last_cross_impl = "tcgen05";
+    return ief_cross_tc_launch(p, st);
+  }
+  g_last_cross_impl = "mma";
   dim3 grid(ief_ceil_div(p->Nq, kBM), p->H, p->B);
   return p->dtype == IEF_BF16 ? launch_flavour<IEF_BF16>(a, flavour, grid, st) : launch_flavour<IEF_F16>(a, flavour, grid, st);
 }

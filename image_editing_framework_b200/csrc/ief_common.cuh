@@ -47,6 +47,7 @@ template <int DTYPE> struct ElemT;
 template <> struct ElemT<IEF_BF16> {
   using T = __nv_bfloat16;
   using T2 = __nv_bfloat162;
+  static constexpr bool kIsBf16 = true;
   static __device__ __forceinline__ uint32_t pack(float lo, float hi) {
     uint32_t r;
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
@@ -58,6 +59,7 @@ template <> struct ElemT<IEF_BF16> {
 template <> struct ElemT<IEF_F16> {
   using T = __half;
   using T2 = __half2;
+  static constexpr bool kIsBf16 = false;
   static __device__ __forceinline__ uint32_t pack(float lo, float hi) {
     uint32_t r;
     asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));

@@ -20,6 +20,16 @@ class FusedDDIM:
     build (p2p/edit_real.py:58-69)."""
 
     def __init__(self, scheduler):
+        # scheduler.step honours these switches; the fused kernel implements exactly one setting of each, so anything else is refused
+        # rather than silently computed differently (SD-2.1-768 checkpoints ship v_prediction, a default-constructed diffusers
+        # DDIMScheduler has clip_sample=True)
+        cfg = scheduler.config
+        get = cfg.get if hasattr(cfg, "get") else (lambda k, d=None: getattr(cfg, k, d))
+        unsupported = [f"{k}={get(k)!r}" for k, ok in (("prediction_type", ("epsilon", None)), ("clip_sample", (False, None)),
+                                                       ("thresholding", (False, None))) if get(k) not in ok]
+        if unsupported:
+            raise ValueError("the fused CFG + DDIM step implements epsilon prediction without sample clipping / thresholding (the scheduler "
+                             "the reference's scripts build, p2p/edit_real.py:58-69); this scheduler has " + ", ".join(unsupported))
         self.scheduler = scheduler
         self._alphas: List[float] = [float(a) for a in scheduler.alphas_cumprod.tolist()]
         self._final = float(scheduler.final_alpha_cumprod)
@@ -56,7 +66,7 @@ class ddim_inversion:
     """Same method names as the reference class (*/inversion/ddim.py:7-58); only the arithmetic moved to the kernel.
 
     `graphs` (an extension, off by default; set it on the class or an instance): the inversion's UNet forwards are replayed from a
-    CUDA graph kept on the UNet. Only while no attention controller is registered — a replay would skip its counters."""
+    CUDA graph kept on the UNet (one runner per installed controller; a controller whose graph_key() is None runs eagerly)."""
 
     graphs = False
 
@@ -74,17 +84,29 @@ class ddim_inversion:
         uncond = model.text_encoder(un.input_ids.to(model.device))[0]
         return torch.cat([uncond, cond])
 
+    def _runner(self, model, latent, unet_kwargs):
+        """The CUDA-graph runner of an inversion (graphs=True only): kept on the UNet, one per installed controller. With no
+        controller registered the UNet's own attention is replayed; with one (e.g. a do-nothing masactrl.AttentionBase, which
+        routes the inversion's attention through the fused kernels) its graph_key() names the phase like in the edit loops."""
+        extras = [v for k, v in unet_kwargs.items() if k != "encoder_hidden_states"]
+        if not (self.graphs and latent.is_cuda and all(v is None for v in extras)):
+            return None
+        from . import _cabi
+        from .graphs import GraphedUNet
+        installed = getattr(model.unet, "_ief_installed", None)
+        runners = model.unet.__dict__.setdefault("_ief_inversion_runners", {})
+        runner = runners.get(id(installed))
+        if runner is None or runner.unet is not model.unet or runner.controller is not installed:
+            if len(runners) >= 4:       # bounded: each runner pins a private graph memory pool
+                runners.pop(next(iter(runners))).close()
+            runner = runners[id(installed)] = GraphedUNet(model.unet, installed, launch_counter=_cabi.launch_count)
+        return runner
+
     def _invert(self, model, latent, unet_kwargs):
         """The loop both classes share: the scheduler's timesteps walked backwards, one UNet forward + one fused reverse step each."""
         trajectory = [latent]
         latent = latent.clone().detach()
-        runner = None
-        extras = [v for k, v in unet_kwargs.items() if k != "encoder_hidden_states"]
-        if self.graphs and latent.is_cuda and all(v is None for v in extras) and getattr(model.unet, "_ief_installed", None) is None:
-            from .graphs import GraphedUNet
-            runner = getattr(model.unet, "_ief_plain_runner", None)
-            if runner is None or runner.unet is not model.unet:
-                runner = model.unet._ief_plain_runner = GraphedUNet(model.unet)
+        runner = self._runner(model, latent, unet_kwargs)
         for t in reversed(model.scheduler.timesteps.tolist()):   # one host copy instead of a device sync per step
             noise_pred = runner(latent, t, unet_kwargs["encoder_hidden_states"]) if runner is not None else \
                 model.unet(latent, t, **unet_kwargs).sample

@@ -250,6 +250,8 @@ const char* ief_last_error(void);
 int64_t ief_launch_count(void);
 /* name of the kernel family the last ief_attn_fwd call dispatched to ("tcgen05" / "mma") */
 const char* ief_last_attn_impl(void);
+/* the same for the last ief_cross_attn_edit_fwd call of this thread ("tcgen05" = cross_tc.cu, "mma" = cross_attn.cu) */
+const char* ief_last_cross_impl(void);
 /* 0 when a CUDA device with compute capability 10.x is current */
 int ief_check_device(void);
 

@@ -20,11 +20,19 @@ def _as3(t, heads):
     return t
 
 
+# bench.py's reference-formulation arms set this (patched(reference_work=True)): the reference closure materialises `sim` and `attn`
+# for EVERY layer before it calls the editor (masactrl/model/register.py:35-44), and a controlled layer then recomputes its own
+# probabilities (attention_control.py:37-50) — so a controlled layer costs the plain probabilities (discarded) on top of the indexed ones.
+REFERENCE_WORK = False
+
+
 def attention(q, k, v, heads, scale, *, q_src=None, k_src=None, v_src=None, k_src2=None, v_src2=None, impl=0, probs_out=None,
               probs_accum=False, probs_slot=None, rows=None, key_bias=None, bias_sel=None, out=None):
     q, k, v = _as3(q, heads), _as3(k, heads), _as3(v, heads)
     B = q.shape[0]
     ident = list(range(B))
+    if REFERENCE_WORK and (q_src is not None or k_src is not None or v_src is not None):
+        orc.attention_probs(q, k, heads, scale)      # the closure's own sim + attn, thrown away by the editor
     qq, kk, vv = q[list(q_src or ident)], k[list(k_src or ident)], v[list(v_src or ident)]
     if k_src2 is not None:
         kk, vv = torch.cat([kk, k[list(k_src2)]], 1), torch.cat([vv, v[list(v_src2)]], 1)
@@ -121,17 +129,21 @@ def install(monkeypatch):
 
 
 @contextlib.contextmanager
-def patched():
-    """bench.py flavour: route the host logic to the CPU oracle inside the `with` block only."""
+def patched(reference_work: bool = False):
+    """bench.py flavour: route the host logic to the oracle (torch fp32 on whatever device the tensors live on) inside the `with`
+    block only. reference_work: also spend the work the reference spends and discards (see REFERENCE_WORK)."""
+    global REFERENCE_WORK
     from image_editing_framework_b200 import hooks
     saved = {n: getattr(real_ops, n) for n in _NAMES}
-    saved_dt = hooks.compute_dtype
+    saved_dt, saved_rw = hooks.compute_dtype, REFERENCE_WORK
     try:
+        REFERENCE_WORK = reference_work
         hooks.compute_dtype = lambda t: t.dtype
         for n in _NAMES:
             setattr(real_ops, n, globals()[n])
         yield
     finally:
         hooks.compute_dtype = saved_dt
+        REFERENCE_WORK = saved_rw
         for n, f in saved.items():
             setattr(real_ops, n, f)

@@ -477,6 +477,32 @@ def gen_pipelines():
     _save("pipelines.pt", out)
 
 
+def gen_fullgeo():
+    """Whole edits at the BASELINE attention geometry (64x64 latents; head dims 40 / 80 / 160 and 64) through the reference's own
+    register closures + controllers + P2P.diffusion_step, fp32 on the CPU (tests/scenarios.py::run_fullgeo with api = the reference's
+    modules). One file per (config, scenario); per-layer outputs are kept on 16 token rows at the last step."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import time
+    import scenarios
+    only = os.environ.get("FULLGEO_ONLY")
+    for cfg_name, kind in scenarios.FULLGEO_CASES:
+        if only and only not in f"{cfg_name}:{kind}":
+            continue
+        t0 = time.time()
+        family = {"p2p": "p2p", "masactrl": "masactrl", "pnp": "pnp"}[kind.split("_")[0]]
+        ctrl, records, per_step = scenarios.run_fullgeo(cfg_name, kind, load_reference(family), CPU, fused_step=False)
+        g = dict(config=scenarios.FULLGEO_CONFIGS[cfg_name], kind=kind, steps=scenarios.FULLGEO_STEPS, rows=scenarios.FULLGEO_ROWS,
+                 layer_outputs=records, latents_per_step=per_step)
+        if kind == "p2p_store":
+            avg = ctrl.get_average_attention()
+            # the 16x16 cross maps (what LocalBlend / MaskAuto read) in full, the larger stored maps on a strip of query rows
+            g["average_attention"] = {k: [t[:, ::max(1, t.shape[1] // 8)].clone() for t in v] for k, v in avg.items()}
+        if ctrl is not None:
+            g["cur_step"] = ctrl.cur_step
+        _save(f"fullgeo_{cfg_name}_{kind}.pt", g)
+        print(f"   ({time.time() - t0:.0f} s)")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     which = sys.argv[1:] or ["aligner", "oracle_pins", "ddim", "p2p", "masactrl", "pnp", "pnp_xl", "pix2pix_zero", "p2p_localblend", "masactrl_masks", "pix2pix_zero_loop", "pipelines"]

@@ -299,3 +299,92 @@ def mirror_api(family):
     import image_editing_framework_b200 as pkg
     mod = {"p2p": pkg.p2p, "masactrl": pkg.masactrl, "pnp": pkg.pnp, "pix2pix-zero": pkg.pix2pix_zero}[family]
     return SimpleNamespace(sd_utils=mod, attention_control=mod, register=mod)
+
+
+# --------------------------------------------------------------------------------- full-geometry scenarios (64x64 latents, real head dims)
+# Slim-channel stand-ins whose ATTENTION geometry is the real one: 64x64 latents (N = 4096 / 1024 / 256 / 64 tokens) and the real
+# head dims — SD-1.5's 40 / 80 / 160 / 160, and 64 everywhere like SD-2.1 / SDXL — with 2-8 heads instead of 8-20 so that the reference's
+# materialised fp32 probabilities fit a CPU run. Large layers therefore take the tcgen05 kernels, small ones the mma.sync ones, exactly
+# as at full width.
+FULLGEO_CONFIGS = {
+    "sd15_slim": dict(sample_size=64, block_out_channels=(80, 160, 320, 320), num_heads=(2, 2, 2, 2), cross_attention_dim=64,
+                      norm_num_groups=8, name="sd15_slim"),
+    "d64_slim": dict(sample_size=64, block_out_channels=(128, 256, 512, 512), num_heads=(2, 4, 8, 8), cross_attention_dim=64,
+                     norm_num_groups=8, use_linear_projection=True, name="d64_slim"),
+}
+FULLGEO_CASES = [("sd15_slim", "p2p_replace"), ("sd15_slim", "p2p_refine"), ("sd15_slim", "p2p_store"), ("sd15_slim", "masactrl"),
+                 ("sd15_slim", "pnp"), ("d64_slim", "p2p_refine"), ("d64_slim", "masactrl"), ("d64_slim", "pnp")]
+FULLGEO_STEPS, FULLGEO_ROWS, FULLGEO_GUIDANCE = 3, 16, 7.5
+FULLGEO_PROMPTS = {"p2p_replace": ["a photo of a cat sitting on a bench", "a photo of a dog sitting on a bench"],
+                   "p2p_refine": ["a bowl of soup", "a bowl of pea soup"],
+                   "p2p_store": ["a photo of a cat sitting on a bench", "a photo of a dog sitting on a bench"],
+                   "masactrl": ["a photo of a sitting cat", "a photo of a running cat"],
+                   "pnp": ["a photo of a wooden horse", "a photo of a bronze horse"]}
+
+
+class RowRecorder:
+    """Like Recorder, but keeps FULLGEO_ROWS evenly spaced token rows of every attention output (a 64x64 layer's full output is 5 MB)."""
+
+    def __init__(self, unet, keep):
+        self.keep, self.step, self.records, self.tokens = set(keep), 0, {}, []
+        for m in unet.modules():
+            if type(m).__name__ == "Attention":
+                m.forward = self._wrap(m.forward)
+
+    def _wrap(self, inner):
+        def fwd(*a, **kw):
+            out = inner(*a, **kw)
+            if self.step in self.keep:
+                n = out.shape[1]
+                rows = torch.linspace(0, n - 1, min(n, FULLGEO_ROWS)).long().to(out.device)
+                self.records.setdefault(self.step, []).append(out.detach().index_select(1, rows).float().cpu())
+            return out
+        return fwd
+
+
+def run_fullgeo(cfg_name, kind, api, device, fused_step=True):
+    """One scenario written against `api` = the reference's modules of the family (oracle.reference_loader, CPU fp32: the golden
+    generator) or this package's mirror (the GPU test). Loop shape: p2p/model/sd_utils.py:67-79 (diffusion_step), masactrl/model/
+    sd_utils.py:107-113, pnp/model/sd_utils.py:99-107. Returns (controller or None, {step: [rows of each layer output]}, latents per step)."""
+    pipe = make_pipeline(UNetConfig(**FULLGEO_CONFIGS[cfg_name]), seed=21, device=device)
+    steps, prompts = FULLGEO_STEPS, FULLGEO_PROMPTS[kind]
+    pipe.scheduler.set_timesteps(steps)
+    hw = 64
+    ctrl = None
+    family = kind.split("_")[0]
+    if family == "p2p":
+        common = dict(prompts=prompts, tokenizer=pipe.tokenizer, num_steps=steps, cross_replace_steps=0.8, self_replace_steps=0.6, device=device)
+        ctrl = {"p2p_replace": lambda: api.attention_control.AttentionReplace(**common),
+                "p2p_refine": lambda: api.attention_control.AttentionRefine(**common),
+                "p2p_store": lambda: api.attention_base.AttentionStore(False)}[kind]()
+        driver = api.sd_utils.P2P(pipe, steps)
+        api.register.register_attention_control(pipe, ctrl)
+    elif family == "masactrl":
+        ctrl = api.attention_control.MutualSelfAttentionControl(1, 10, total_steps=steps)
+        api.register.regiter_attention_editor_diffusers(pipe, ctrl)
+    else:
+        ts = pipe.scheduler.timesteps
+        api.register.register_attention_control_efficient(pipe, ts[:int(steps * 0.5)])
+        api.register.register_conv_control_efficient(pipe, ts[:int(steps * 0.8)])
+    rec = RowRecorder(pipe.unet, (steps - 1,))
+    context = editing.encode_prompts(pipe, prompts)
+    init = latent(31, (1, 4, hw, hw), device)
+    latents = torch.cat([init, init])
+    fused = FusedDDIM(pipe.scheduler) if fused_step else None
+    per_step = []
+    with torch.no_grad():
+        for i, t in enumerate(pipe.scheduler.timesteps):
+            rec.step = i
+            if family == "p2p":
+                latents = driver.diffusion_step(pipe, ctrl, latents, context, t if not fused_step else int(t), FULLGEO_GUIDANCE, False)
+            else:
+                if family == "pnp":
+                    api.register.register_time(pipe, t.item())
+                noise = pipe.unet(torch.cat([latents] * 2), t if not fused_step else int(t), encoder_hidden_states=context).sample
+                if fused_step:
+                    latents = fused.step(noise, int(t), latents, FULLGEO_GUIDANCE)
+                else:
+                    nu, nc = noise.chunk(2)
+                    latents = pipe.scheduler.step(nu + FULLGEO_GUIDANCE * (nc - nu), t, latents).prev_sample
+            per_step.append(latents.float().cpu())
+    return ctrl, rec.records, per_step

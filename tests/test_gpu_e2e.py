@@ -405,9 +405,20 @@ def test_ddim_inversion_graph_replay_matches_eager(cuda):
     inv = ddim_inversion()
     inv.graphs = True
     got, _ = inv.ddim_inversion_loop(pipe, x0, scenarios.PIPELINE_PROMPTS[:1])
-    runner = pipe.unet._ief_plain_runner
+    runner = pipe.unet._ief_inversion_runners[id(None)]
     assert runner.replays >= 6 and runner.captures == 1
     assert len(got) == len(want) == 9 and all(torch.allclose(a, b, atol=1e-4, rtol=1e-4) for a, b in zip(got, want))
+    # with a do-nothing editor registered the inversion's attention runs on the fused kernels and is replayed all the same
+    import image_editing_framework_b200 as pkg
+    plain = pkg.masactrl.AttentionBase()
+    pkg.masactrl.regiter_attention_editor_diffusers(pipe, plain)
+    try:
+        hooked, _ = inv.ddim_inversion_loop(pipe, x0, scenarios.PIPELINE_PROMPTS[:1])
+    finally:
+        pkg.masactrl.unregister_attention_control(pipe, plain)
+    runner = pipe.unet._ief_inversion_runners[id(plain)]
+    assert runner.replays >= 6 and runner.captures == 1 and plain.cur_step == 8
+    assert psnr(hooked[-1].float(), want[-1].float()) >= PSNR_DB
 
 
 def test_xl_pipeline_class_graph_replay_carries_added_cond_kwargs(cuda):
@@ -433,3 +444,70 @@ def test_xl_pipeline_class_graph_replay_carries_added_cond_kwargs(cuda):
         got = edit(graphed)
         assert abs(got.astype("int16") - want.astype("int16")).max() <= 1
     assert graphed._runner.replays > steps
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE attention geometry
+class _ImplLog:
+    """Records which kernel family served every ops.attention / ops.cross_attention_edit call (token count, head_dim, impl name)."""
+
+    def __init__(self):
+        from image_editing_framework_b200 import ops
+        self.ops, self.calls = ops, []
+        self._attn, self._cross = ops.attention, ops.cross_attention_edit
+
+    def __enter__(self):
+        def attention(q, k, v, heads, scale, **kw):
+            out = self._attn(q, k, v, heads, scale, **kw)
+            self.calls.append(("self", q.shape[1], q.shape[2] // heads if q.dim() == 3 else q.shape[3], _cabi.last_attn_impl()))
+            return out
+
+        def cross(q, k, v, heads, scale, **kw):
+            out = self._cross(q, k, v, heads, scale, **kw)
+            self.calls.append(("cross", q.shape[1], q.shape[2] // heads if q.dim() == 3 else q.shape[3], _cabi.last_cross_impl()))
+            return out
+        self.ops.attention, self.ops.cross_attention_edit = attention, cross
+        return self
+
+    def __exit__(self, *a):
+        self.ops.attention, self.ops.cross_attention_edit = self._attn, self._cross
+
+
+@pytest.mark.parametrize("cfg_name,kind", scenarios.FULLGEO_CASES)
+def test_edits_at_baseline_attention_geometry_match_reference(cuda, cfg_name, kind):
+    """64x64 latents with the real head dims (SD-1.5's 40 / 80 / 160, and 64): whole edits through this package's register closures,
+    controllers and kernels against runs of the REFERENCE's own closures + controllers + diffusion_step on the same stand-in, fp32 on
+    the CPU (tests/golden/fullgeo_*.pt, make_goldens.py::gen_fullgeo). Gates: every attention layer output of the last step within
+    2e-2 max-abs (16 token rows per layer), final latents >= 40 dB, and the large layers served by the tcgen05 kernels."""
+    import image_editing_framework_b200 as pkg
+    g = golden(f"fullgeo_{cfg_name}_{kind}.pt")
+    api = {"p2p": pkg.p2p, "masactrl": pkg.masactrl, "pnp": pkg.pnp}[kind.split("_")[0]]
+    with _ImplLog() as log:
+        ctrl, records, per_step = scenarios.run_fullgeo(cfg_name, kind, api, cuda)
+    worst = 0.0
+    for step, outs in g["layer_outputs"].items():
+        got = records[step]
+        assert len(got) == len(outs) == 32
+        for i, (a, b) in enumerate(zip(got, outs)):
+            err = (a - b).abs().max().item()
+            worst = max(worst, err)
+            assert err < LAYER_TOL, f"step {step} layer {i} ({tuple(b.shape)}): max abs err {err}"
+    for i, (a, b) in enumerate(zip(per_step, g["latents_per_step"])):
+        db = psnr(a, b)
+        assert db >= PSNR_DB, f"latents after step {i}: PSNR {db:.1f} dB"
+    if "cur_step" in g:
+        assert ctrl.cur_step == g["cur_step"]
+    # the kernels that matter at this geometry really ran: tcgen05 for every self-attention layer with >= 1024 tokens (with the
+    # probability sweep behind it where maps are stored), and for the plain cross-attention rows of the large layers
+    big_self = [c for c in log.calls if c[0] == "self" and c[1] >= 1024]
+    assert big_self and all(c[3] in ("tcgen05", "tcgen05+probs") for c in big_self), sorted(set(big_self))
+    if kind in ("masactrl", "pnp"):
+        big_cross = [c for c in log.calls if c[0] == "cross" and c[1] >= 1024]
+        assert big_cross and all(c[3] == "tcgen05" for c in big_cross), sorted(set(big_cross))
+    if kind == "p2p_store":
+        avg = ctrl.get_average_attention()
+        for key, maps in g["average_attention"].items():
+            assert len(avg[key]) == len(maps)
+            for a, b in zip(avg[key], maps):
+                a = a.float().cpu()
+                assert (a[:, ::max(1, a.shape[1] // 8)] - b).abs().max().item() < LAYER_TOL, key
+    print(f"{cfg_name}/{kind}: worst layer err {worst:.4f}, final PSNR {psnr(per_step[-1], g['latents_per_step'][-1]):.1f} dB")

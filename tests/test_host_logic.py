@@ -555,3 +555,17 @@ def test_reference_script_flow_after_import_switch(monkeypatch):
         unregister_attention_control(pipe, controller)
         assert images.shape == (2, 64, 64, 3) and images.dtype == np.uint8 and controller.cur_step == steps
         assert not np.array_equal(images[0], images[1])       # two prompts, two images
+
+
+@pytest.mark.parametrize("field,value", [("prediction_type", "v_prediction"), ("clip_sample", True), ("thresholding", True)])
+def test_fused_ddim_refuses_scheduler_configs_it_does_not_implement(field, value):
+    """scheduler.step honours prediction_type / clip_sample / thresholding (p2p/model/sd_utils.py:76 calls it); the fused step implements
+    the one configuration the reference's scripts build (p2p/edit_real.py:58-69) and must say so for any other."""
+    from image_editing_framework_b200.ddim import FusedDDIM
+    from image_editing_framework_b200.standin.pipeline import DDIMScheduler
+    sched = DDIMScheduler()
+    sched.set_timesteps(10)
+    FusedDDIM(sched)                                   # the scripts' configuration is accepted
+    setattr(sched.config, field, value)
+    with pytest.raises(ValueError, match=field):
+        FusedDDIM(sched)
