@@ -11,7 +11,7 @@ FLAGS+=("${EXTRA[@]}")
 objs=()
 pids=()
 mkdir -p "$here/build"
-for f in api attn_tc attn_tc2 attn_tc3 attn_mma cross_attn cross_tc cross_attn_bwd elementwise; do
+for f in api attn_tc attn_tc2 attn_tc3 attn_mma cross_attn cross_tc cross_tc_edit cross_attn_bwd elementwise; do
   "$NVCC" "${FLAGS[@]}" -c "$here/$f.cu" -o "$here/build/$f.o" &
   pids+=($!)
   objs+=("$here/build/$f.o")

@@ -17,9 +17,11 @@
 // Shared memory is sized per mode (25 KB for plain rows at head_dim 40), so 4-8 CTAs are resident per SM.
 #include "mma_utils.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 bool ief_cross_tc_supported(const ief_cross_params* p);
-int ief_cross_tc_launch(const ief_cross_params* p, cudaStream_t st);
+int ief_cross_tc_launch(const ief_cross_params* p, cudaStream_t st, const int32_t* rows = nullptr, int n_rows = 0);
+int ief_cross_tc_edit_launch(const ief_cross_params* p, const int32_t* rows, int n_rows, cudaStream_t st);
 
 using namespace mmau;
 
@@ -337,10 +339,30 @@ extern "C" int ief_cross_attn_edit_fwd(const ief_cross_params* p, void* stream) 
     flavour = (p->mode == IEF_EDIT_REPLACE && !(p->mapper_nz_idx && p->mapper_nz_w)) ? kEditDense : kEditGather;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  // un-edited rows without a map output: the tcgen05 kernel (cross_tc.cu), a row per thread instead of a row per quad
-  if (flavour == kPlain && p->probs_out == nullptr && ief_cross_tc_supported(p)) {
-    g_last_cross_impl = "tcgen05";
-    return ief_cross_tc_launch(p, st);
+  // Tensor-pipe kernels (>= 128 queries): un-edited rows without a map output on cross_tc.cu, edited and / or stored rows on
+  // cross_tc_edit.cu (sparse replace mapper, refine gather, reweight, alpha blend, store epilogue). What stays on this file's
+  // mma.sync kernel: layers with fewer than 128 queries (8x8 latents) and the dense 77x77 mapper fallback.
+  if (flavour != kEditDense && ief_cross_tc_supported(p)) {
+    static int edit_on = -1;
+    if (edit_on < 0) { const char* e = getenv("IEF_CROSS_TC_EDIT"); edit_on = (e && e[0] == '0') ? 0 : 1; }
+    int32_t special[IEF_MAX_ROWS], plain[IEF_MAX_ROWS];
+    int ns = 0, np = 0;
+    for (int i = 0; i < p->B; ++i)   // edited rows first: their CTAs run longest
+      if (a.base_row[i] >= 0) special[ns++] = i;
+    for (int i = 0; i < p->B; ++i) {
+      if (a.base_row[i] >= 0) continue;
+      if (p->probs_out != nullptr && a.store_slot[i] >= 0) special[ns++] = i; else plain[np++] = i;
+    }
+    if (ns == 0) {
+      g_last_cross_impl = "tcgen05";
+      return ief_cross_tc_launch(p, st);
+    }
+    if (edit_on) {
+      g_last_cross_impl = "tcgen05-edit";
+      int rc = ief_cross_tc_edit_launch(p, special, ns, st);
+      if (rc != IEF_OK || np == 0) return rc;
+      return ief_cross_tc_launch(p, st, plain, np);
+    }
   }
   g_last_cross_impl = "mma";
   dim3 grid(ief_ceil_div(p->Nq, kBM), p->H, p->B);

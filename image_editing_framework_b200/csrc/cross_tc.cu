@@ -31,6 +31,7 @@ struct CrossTcArgs {
   uint32_t idesc_qk, idesc_pv;
   float scale_log2;
   int32_t perm_q[3], perm_k[3], perm_v[3];
+  int32_t row[IEF_MAX_ROWS];   // blockIdx.z -> batch row (a call may hand its edited / stored rows to cross_tc_edit.cu)
 };
 
 template <int DCH> constexpr int cross_tc_smem() { return DCH * (2 * kQChunk + 2 * kKVChunk) + 1024 + 128; }
@@ -41,7 +42,7 @@ cross_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 const __grid_constant__ CrossTcArgs a) {
   using E = ElemT<DTYPE>;
   constexpr int kTmemCols = TCOLS;   // 128 when 80 + dv <= 128 (head_dim <= 48), else 256
-  const int b = blockIdx.z, h = blockIdx.y;
+  const int b = a.row[blockIdx.z], h = blockIdx.y;
   const int nqt = (a.Nq + kBM - 1) / kBM;
   const int qt0 = blockIdx.x * a.tiles_per_cta, ntile = min(a.tiles_per_cta, nqt - qt0);
   extern __shared__ uint8_t smem_raw[];
@@ -223,8 +224,10 @@ bool ief_cross_tc_supported(const ief_cross_params* p) {
   return on && p->Nk <= kNK && p->d % 8 == 0 && p->d >= 8 && p->d <= 160 && p->Nq >= kBM && (p->dtype == IEF_BF16 || p->dtype == IEF_F16);
 }
 
-int ief_cross_tc_launch(const ief_cross_params* p, cudaStream_t st) {
+int ief_cross_tc_launch(const ief_cross_params* p, cudaStream_t st, const int32_t* rows, int n_rows) {
   CrossTcArgs a;
+  const int nb = rows ? n_rows : p->B;
+  for (int i = 0; i < IEF_MAX_ROWS; ++i) a.row[i] = i < nb ? (rows ? rows[i] : i) : 0;
   a.o = p->o.ptr; a.o_sb = p->o.stride_b; a.o_sn = p->o.stride_n; a.o_sh = p->o.stride_h;
   a.B = p->B; a.H = p->H; a.Nq = p->Nq; a.Nk = p->Nk; a.d = p->d;
   a.ksteps_qk = ief_ceil_div(p->d, 16);
@@ -244,11 +247,11 @@ int ief_cross_tc_launch(const ief_cross_params* p, cudaStream_t st) {
   const int sms = ief_sm_count();
   const int nqt = ief_ceil_div(p->Nq, kBM);
   const long slots = (long)sms * (cfg == 0 ? 4 : 2);
-  int tpc = (int)(((long)nqt * p->H * p->B + slots - 1) / slots);
+  int tpc = (int)(((long)nqt * p->H * nb + slots - 1) / slots);
   tpc = tpc < 1 ? 1 : (tpc > 8 ? 8 : tpc);
   if (tpc > nqt) tpc = nqt;
   a.tiles_per_cta = tpc;
-  dim3 grid(ief_ceil_div(nqt, tpc), p->H, p->B);
+  dim3 grid(ief_ceil_div(nqt, tpc), p->H, nb);
   if (p->dtype == IEF_BF16) {
     switch (cfg) {
       case 0: return launch_cross_tc<IEF_BF16, 1, 128>(mq, mk, mv, a, grid, st);

@@ -238,6 +238,7 @@ class AttentionControlEdit(AttentionStore, abc.ABC):
                  local_blend: Optional[LocalBlend], device=torch.device("cuda:0"), LOW_RESOURCE=False):
         super().__init__(LOW_RESOURCE)
         self.batch_size = len(prompts)
+        self._num_steps, self._cross_replace_steps = num_steps, cross_replace_steps
         self.cross_replace_alpha = ptp_utils.get_time_words_attention_alpha(prompts, num_steps, cross_replace_steps, tokenizer).to(device)
         if type(self_replace_steps) is float:
             self_replace_steps = 0, self_replace_steps
@@ -290,11 +291,32 @@ class AttentionControlEdit(AttentionStore, abc.ABC):
             x_t = self.local_blend(x_t, self.attention_store)
         return x_t
 
+    # ---- extension (not in the reference): one controller, many prompt pairs ------------------------------------------
+    _tables_epoch = 0
+
+    def retarget(self, prompts, tokenizer) -> None:
+        """Re-point this controller at another prompt set of the same size: the alpha schedule and the edit tables are recomputed
+        on the host exactly as the constructor does and written INTO the existing device buffers, so CUDA graphs captured with this
+        controller stay valid (the sweeps of */test.py build a new controller per image; with graphs that would re-capture every
+        time). Falls back to fresh buffers — and a new graph key — when a table changes shape or form. Counters are reset."""
+        if len(prompts) != self.batch_size:
+            raise ValueError(f"retarget: controller was built for {self.batch_size} prompts, got {len(prompts)}")
+        if self.local_blend is not None:
+            raise NotImplementedError("retarget: a LocalBlend is tied to its prompts; build a new controller")
+        alpha = ptp_utils.get_time_words_attention_alpha(prompts, self._num_steps, self._cross_replace_steps, tokenizer).to(self._device)
+        self.cross_replace_alpha.copy_(alpha)
+        self._alpha_table.copy_(alpha.reshape(self._alpha_table.shape).to(torch.float32))
+        self._retarget_tables(prompts, tokenizer)
+        self.reset()
+
+    def _retarget_tables(self, prompts, tokenizer) -> None:
+        raise NotImplementedError(f"{type(self).__name__} does not support retarget()")
+
     def graph_key(self):
         base = super().graph_key()
         if base is None or self.cur_step >= self._alpha_table.shape[0]:
             return None
-        return base + (self.num_self_replace[0] <= self.cur_step < self.num_self_replace[1],)
+        return base + (self.num_self_replace[0] <= self.cur_step < self.num_self_replace[1], self._tables_epoch)
 
     def graph_prepare(self) -> None:
         if self._graph_mode and self.cur_step < self._alpha_table.shape[0]:

@@ -62,6 +62,20 @@ class AttentionReplace(AttentionControlEdit):
         # CrossEdit derives the sparse (<= 8 source tokens per target token) form the kernel prefers from the dense mapper
         return ops.CrossEdit(ops.IEF_EDIT_REPLACE, self.mapper.shape[0], mapper=_f32(self.mapper))
 
+    def _retarget_tables(self, prompts, tokenizer) -> None:
+        aligned = seq_aligner.get_replacement_mapper(prompts, tokenizer)
+        self.mapper.copy_(_expect(aligned, tuple(self.mapper.shape), "replacement mapper"))
+        if self._edit is None:
+            return
+        fresh = ops.CrossEdit(ops.IEF_EDIT_REPLACE, self.mapper.shape[0], mapper=_f32(self.mapper))
+        if (fresh.mapper_nz_idx is None) != (self._edit.mapper_nz_idx is None):
+            self._edit, self._tables_epoch = fresh, self._tables_epoch + 1     # sparse <-> dense form: other kernel flavour, new graphs
+            return
+        self._edit.mapper.copy_(fresh.mapper)
+        if fresh.mapper_nz_idx is not None:
+            self._edit.mapper_nz_idx.copy_(fresh.mapper_nz_idx)
+            self._edit.mapper_nz_w.copy_(fresh.mapper_nz_w)
+
 
 class AttentionRefine(AttentionControlEdit):
     """Prompt refinement: target tokens aligned to a source token take its probability (gather), new tokens keep their own."""
@@ -90,6 +104,16 @@ class AttentionRefine(AttentionControlEdit):
         targets = self.mapper.shape[0]
         return ops.CrossEdit(ops.IEF_EDIT_REFINE, targets, mapper_idx=self.mapper.to(torch.int32).contiguous(),
                              refine_alpha=_f32(self.alphas.reshape(targets, -1)))
+
+    def _retarget_tables(self, prompts, tokenizer) -> None:
+        gather_idx, keep = seq_aligner.get_refinement_mapper(prompts, tokenizer)
+        if int(gather_idx.min()) < -1 or int(gather_idx.max()) >= gather_idx.shape[-1]:
+            raise ValueError("refinement mapper holds token positions outside [-1, max_length)")
+        self.mapper.copy_(_expect(gather_idx, tuple(self.mapper.shape), "refinement mapper"))
+        self.alphas.copy_(keep.reshape(self.alphas.shape))
+        if self._edit is not None:
+            self._edit.mapper_idx.copy_(self.mapper.to(torch.int32))
+            self._edit.refine_alpha.copy_(self.alphas.reshape(self.mapper.shape[0], -1).to(torch.float32))
 
 
 class AttentionReweight(AttentionControlEdit):

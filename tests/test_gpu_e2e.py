@@ -500,7 +500,7 @@ def test_edits_at_baseline_attention_geometry_match_reference(cuda, cfg_name, ki
     # probability sweep behind it where maps are stored), and for the plain cross-attention rows of the large layers
     big_self = [c for c in log.calls if c[0] == "self" and c[1] >= 1024]
     assert big_self and all(c[3] in ("tcgen05", "tcgen05+probs") for c in big_self), sorted(set(big_self))
-    if kind in ("masactrl", "pnp"):
+    if kind == "masactrl":       # (PnP hooks eight self-attention layers only: its cross-attention stays the UNet's own)
         big_cross = [c for c in log.calls if c[0] == "cross" and c[1] >= 1024]
         assert big_cross and all(c[3] == "tcgen05" for c in big_cross), sorted(set(big_cross))
     if kind == "p2p_store":
@@ -511,3 +511,52 @@ def test_edits_at_baseline_attention_geometry_match_reference(cuda, cfg_name, ki
                 a = a.float().cpu()
                 assert (a[:, ::max(1, a.shape[1] // 8)] - b).abs().max().item() < LAYER_TOL, key
     print(f"{cfg_name}/{kind}: worst layer err {worst:.4f}, final PSNR {psnr(per_step[-1], g['latents_per_step'][-1]):.1f} dB")
+
+
+# ------------------------------------------------------------------------------------------------ PIE-Bench-shaped sweep (configs[4])
+def _load_sweep():
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("ief_sweep", os.path.join(root, "tools", "sweep.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_sharded_sweep_reproduces_the_serial_sweep_bit_for_bit(cuda):
+    """tools/sweep.py: a 6-image subset x 4 methods, once as one rank and once as the two shards of a 2-rank sweep (image i -> rank
+    i mod 2, separate pipeline replicas, kept controllers re-pointed with retarget(), CUDA-graph replay on): the uint8 result
+    images must agree bit for bit (CRC per image and method)."""
+    sweep = _load_sweep()
+    methods, n = list(sweep.METHODS), 6
+    make = lambda: sweep.Worker(cuda, 6, True, "tiny", torch.float32)
+    serial = sweep.sweep(make(), n, methods, rank=0, world=1)
+    sharded = {}
+    for rank in range(2):
+        sharded.update(sweep.sweep(make(), n, methods, rank=rank, world=2))
+    assert sorted(sharded) == list(range(n))
+    for i in range(n):
+        assert sharded[i]["crc"] == serial[i]["crc"], (i, sharded[i]["crc"], serial[i]["crc"])
+    eager = sweep.sweep(sweep.Worker(cuda, 6, False, "tiny", torch.float32), 3, methods, rank=0, world=1)
+    for i in range(3):     # replayed graphs launch the same kernels as the eager loop
+        assert {m: eager[i]["crc"][m] for m in ("p2p", "masactrl", "pnp")} == {m: serial[i]["crc"][m] for m in ("p2p", "masactrl", "pnp")}, i
+
+
+def test_two_gpu_sweep_equals_one_gpu_sweep(cuda):
+    """The same through torchrun on two real GPUs (skipped on a one-GPU box): crc_of_crcs of the gathered records."""
+    import json
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    base = [os.path.join(root, "tools", "sweep.py"), "--images", "6", "--ddim-steps", "6", "--config", "tiny"]
+    one = subprocess.run([sys.executable] + base, capture_output=True, text=True, timeout=600, check=True)
+    two = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29631"] + base, capture_output=True, text=True, timeout=600, check=True)
+    a = json.loads([l for l in one.stdout.splitlines() if l.startswith("{")][-1])
+    b = json.loads([l for l in two.stdout.splitlines() if l.startswith("{")][-1])
+    assert a["n_gpus"] == 1 and b["n_gpus"] == 2 and a["images"] == b["images"] == 6
+    assert a["crc_of_crcs"] == b["crc_of_crcs"]

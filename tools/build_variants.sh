@@ -16,7 +16,7 @@ for spec in "$@"; do
   ( "$NVCC" "${FLAGS[@]}" "${D[@]}" -c "$src/attn_tc3.cu" -o "$out/attn_tc3_$name.o"
     "$NVCC" "${FLAGS[@]}" "${D[@]}" -c "$src/api.cu" -o "$out/api_$name.o"   # the trace hook lives in api.cu
     objs=()
-    for f in attn_tc attn_tc2 attn_mma cross_attn cross_tc cross_attn_bwd elementwise; do objs+=("$src/build/$f.o"); done
+    for f in attn_tc attn_tc2 attn_mma cross_attn cross_tc cross_tc_edit cross_attn_bwd elementwise; do objs+=("$src/build/$f.o"); done
     "$NVCC" -shared -o "$out/libief_b200_$name.so" "${objs[@]}" "$out/api_$name.o" "$out/attn_tc3_$name.o" -Xlinker --no-undefined -lcudart_static -lcuda -ldl -lrt -lpthread
     echo "built $out/libief_b200_$name.so" ) &
   pids+=($!)
