@@ -110,16 +110,20 @@ struct LbTable {
   int32_t head_off[16];
   int32_t n_maps, n_prompts, res, n_words, total_heads;
   const float* word_alpha;
-  float* work;  // [n_prompts, res*res], zeroed
+  float* work;  // [n_prompts, res*res], fully written by lb_reduce_kernel
 };
 
-// work[p][pix] += sum over this map's heads and over the selected words of map[p*heads+h][pix][w] * alpha[p][w]
+// work[p][pix] = sum over all maps' heads and over the selected words of map[p*heads+h][pix][w] * alpha[p][w], DETERMINISTIC: a CTA owns
+// 32 pixels of one prompt; its 8 warps split the (map, head) list round-robin in a fixed order and their partial sums are added in
+// warp order — no atomics, so the thresholded mask (and with it an edit) is bit-reproducible run to run, like the reference's
+// `sum(-1).mean(1)`.
 __global__ void __launch_bounds__(256)
 lb_reduce_kernel(const __grid_constant__ LbTable t) {
   __shared__ int s_words[IEF_MAX_WORDS];
   __shared__ float s_alpha[IEF_MAX_WORDS];
   __shared__ int s_nw;
-  const int p = blockIdx.z, mi = blockIdx.y;
+  __shared__ float s_part[8][32];
+  const int p = blockIdx.y;
   if (threadIdx.x == 0) {
     int n = 0;
     for (int w = 0; w < t.n_words; ++w) {
@@ -129,14 +133,27 @@ lb_reduce_kernel(const __grid_constant__ LbTable t) {
     s_nw = n;
   }
   __syncthreads();
-  const int npix = t.res * t.res, heads = t.heads[mi];
-  const float* base = t.maps[mi] + (int64_t)p * heads * npix * t.n_words;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < heads * npix; i += gridDim.x * blockDim.x) {
-    const int hh = i / npix, pix = i - hh * npix;
-    const float* row = base + ((int64_t)hh * npix + pix) * t.n_words;
-    float acc = 0.f;
-    for (int k = 0; k < s_nw; ++k) acc = fmaf(__ldg(row + s_words[k]), s_alpha[k], acc);
-    atomicAdd(t.work + p * npix + pix, acc);
+  const int npix = t.res * t.res, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int pix = blockIdx.x * 32 + lane;
+  float acc = 0.f;
+  if (pix < npix) {
+    for (int j = warp; j < t.total_heads; j += 8) {
+      int mi = 0;
+      while (mi + 1 < t.n_maps && j >= t.head_off[mi + 1]) ++mi;
+      const int heads = t.heads[mi], hh = j - t.head_off[mi];
+      const float* row = t.maps[mi] + (((int64_t)p * heads + hh) * npix + pix) * t.n_words;
+      float part = 0.f;
+      for (int k = 0; k < s_nw; ++k) part = fmaf(__ldg(row + s_words[k]), s_alpha[k], part);
+      acc += part;
+    }
+  }
+  s_part[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && pix < npix) {
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sum += s_part[w][lane];
+    t.work[p * npix + pix] = sum;
   }
 }
 
@@ -325,8 +342,7 @@ extern "C" int ief_local_blend(const ief_local_blend_params* p, void* stream) {
   t.n_maps = p->n_maps; t.n_prompts = p->n_prompts; t.res = p->res; t.n_words = p->n_words; t.total_heads = total;
   t.word_alpha = p->word_alpha; t.work = p->workspace;
   const int npix = p->res * p->res;
-  IEF_CUDA_OK(cudaMemsetAsync(p->workspace, 0, sizeof(float) * p->n_prompts * npix, st));
-  dim3 grid(8, p->n_maps, p->n_prompts);
+  dim3 grid((npix + 31) / 32, p->n_prompts);
   lb_reduce_kernel<<<grid, 256, 0, st>>>(t);
   IEF_LAUNCH_OK("lb_reduce_kernel");
   LbApply a;

@@ -15,11 +15,24 @@ import torch
 _COMPUTE = {"bf16": torch.bfloat16, "fp16": torch.float16}
 
 
+_warned_downcast = False
+
+
 def compute_dtype(t: torch.Tensor) -> torch.dtype:
-    """Kernel arithmetic type: the tensor's own 16-bit type, else IEF_COMPUTE_DTYPE (default bf16)."""
+    """Kernel arithmetic type: the tensor's own 16-bit type, else IEF_COMPUTE_DTYPE (default bf16). An fp32 pipeline (what the
+    reference's scripts build) therefore has its attention — and the stored probability maps that feed the LocalBlend / MaskAuto
+    thresholds and the pix2pix-zero loss — computed from 16-bit q, k, v with fp32 accumulation: within 2e-2 of the fp32 result
+    (the tolerance BASELINE.json states), not bit-equal to it. Said once, loudly, instead of silently."""
+    global _warned_downcast
     if t.dtype in (torch.bfloat16, torch.float16):
         return t.dtype
-    return _COMPUTE[os.environ.get("IEF_COMPUTE_DTYPE", "bf16")]
+    choice = os.environ.get("IEF_COMPUTE_DTYPE", "bf16")
+    if not _warned_downcast:
+        _warned_downcast = True
+        import warnings
+        warnings.warn(f"image_editing_framework_b200: {t.dtype} attention inputs are computed in {choice} on the tensor cores (fp32 accumulation, "
+                      "outputs within 2e-2 of fp32). IEF_COMPUTE_DTYPE=fp16 trades range for 3 more mantissa bits.", stacklevel=3)
+    return _COMPUTE[choice]
 
 
 def _fused_weight(module, names: Tuple[str, ...]):

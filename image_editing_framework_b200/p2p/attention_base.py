@@ -55,6 +55,8 @@ class AttentionControl(abc.ABC):
     # ---- fused entry point used by register_attention_control ---------------------------------------------------
     def attend(self, q, k, v, heads: int, scale: float, is_cross: bool, place_in_unet: str) -> torch.Tensor:
         """Equivalent of `bmm(self(softmax(scale q k^T), is_cross, place_in_unet), v)` on [B, N, H*d] projections."""
+        if self._needs_probabilities():
+            return self._attend_materialised(q, k, v, heads, scale, is_cross, place_in_unet)
         if self.cur_att_layer >= self.num_uncond_att_layers:
             out = self.fused_forward(q, k, v, heads, scale, is_cross, place_in_unet)
         else:
@@ -62,19 +64,56 @@ class AttentionControl(abc.ABC):
         self._tick()
         return out
 
-    @abc.abstractmethod
     def fused_forward(self, q, k, v, heads, scale, is_cross: bool, place_in_unet: str) -> torch.Tensor:
-        raise NotImplementedError
+        raise NotImplementedError(f"{type(self).__name__} defines neither fused_forward() nor the reference's forward(attn, is_cross, place_in_unet)")
 
-    # ---- reference API that has no fused meaning -----------------------------------------------------------------
+    # ---- the reference's materialised-probability interface (attention_base.py:16-32) -----------------------------
+    # Controllers written against the reference implement `forward(attn, is_cross, place_in_unet)` on a [rows*heads, N, M] probability
+    # tensor, or override replace_cross_attention / replace_self_attention of an edit controller. Such code cannot run inside a
+    # fused kernel, so for those controllers (and only for them) the closure takes the compatibility route: the kernel EMITS the
+    # probabilities (its map output), `controller(attn, is_cross, place)` runs exactly as in the reference, and P'V is one batched
+    # GEMM. Cheap for the 77-key cross-attention it is meant for; for self-attention it costs what the reference costs (N x N fp32).
+    def _needs_probabilities(self) -> bool:
+        cls = type(self)
+        cached = cls.__dict__.get("_ief_route")
+        if cached is None:
+            names = ("forward", "replace_cross_attention", "replace_self_attention")
+            cached = any(hasattr(cls, n) and not getattr(getattr(cls, n), "_ief_builtin", False) for n in names)
+            cls._ief_route = cached
+        return cached
+
+    _MATERIALISE_LIMIT_BYTES = 8 << 30
+
+    def _attend_materialised(self, q, k, v, heads, scale, is_cross, place_in_unet):
+        B, N, M = q.shape[0], q.shape[1], k.shape[1]
+        if B * heads * N * M * 4 > self._MATERIALISE_LIMIT_BYTES:
+            raise RuntimeError(f"{type(self).__name__} edits materialised probabilities; this layer's map would be {B * heads} x {N} x {M} fp32 "
+                               f"({B * heads * N * M * 4 / 2 ** 30:.1f} GiB). Implement fused_forward() for layers of this size.")
+        probs = torch.empty((B * heads, N, M), dtype=torch.float32, device=q.device)
+        if is_cross and M <= 80:
+            ops.cross_attention_edit(q, k, v, heads, scale, probs_out=probs)
+        else:
+            ops.attention(q, k, v, heads, scale, probs_out=probs)
+        edited = self(probs, is_cross, place_in_unet)          # reference semantics, counters included
+        v4 = v if v.dim() == 4 else v.view(B, M, heads, -1)
+        out = torch.einsum("bhnm,bmhd->bnhd", edited.view(B, heads, N, M).to(v4.dtype), v4)
+        return out.reshape(B, N, -1)
+
     def __call__(self, attn, is_cross: bool, place_in_unet: str):
-        raise RuntimeError(
-            f"{type(self).__name__}: the materialised-probability entry point controller(attn, is_cross, place) is not served by "
-            "the fused path (no N x N probability tensor exists). Install the controller with register_attention_control; a "
-            "custom controller must implement fused_forward().")
+        """controller(attn, is_cross, place_in_unet) on materialised probabilities, as the reference defines it (:16-28)."""
+        if self.cur_att_layer >= self.num_uncond_att_layers:
+            if self.LOW_RESOURCE:
+                attn = self.forward(attn, is_cross, place_in_unet)
+            else:
+                half = attn.shape[0] // 2
+                attn[half:] = self.forward(attn[half:], is_cross, place_in_unet)   # only the conditional rows are edited
+        self._tick()
+        return attn
 
     def forward(self, attn, is_cross: bool, place_in_unet: str):
-        return self.__call__(attn, is_cross, place_in_unet)
+        raise NotImplementedError
+
+    forward._ief_builtin = True
 
     def step_callback(self, x_t):
         return x_t
@@ -118,6 +157,11 @@ class EmptyControl(AttentionControl):
 
     def fused_forward(self, q, k, v, heads, scale, is_cross, place_in_unet):
         return _plain(q, k, v, heads, scale, is_cross)
+
+    def forward(self, attn, is_cross: bool, place_in_unet: str):
+        return attn
+
+    forward._ief_builtin = True
 
 
 class AttentionStore(AttentionControl):
@@ -180,6 +224,19 @@ class AttentionStore(AttentionControl):
     def fused_forward(self, q, k, v, heads, scale, is_cross, place_in_unet):
         return self._attend_and_store(q, k, v, heads, scale, is_cross, place_in_unet)
 
+    def forward(self, attn, is_cross: bool, place_in_unet: str):
+        """Materialised form (reference :64-68): maps of layers with at most 32^2 queries are summed into `attention_store`."""
+        if self._stores(attn.shape[1]):
+            key = f"{place_in_unet}_{'cross' if is_cross else 'self'}"
+            if self._wanted(attn.shape[1], is_cross):
+                buf, accum = self._store_target(key, attn.shape[0], 1, attn.shape[1], attn.shape[2], attn.device)
+                buf.add_(attn) if accum else buf.copy_(attn)
+            else:
+                self._skip_slot(key)
+        return attn
+
+    forward._ief_builtin = True
+
     def _attend_and_store(self, q, k, v, heads, scale, is_cross, place_in_unet, *, self_src=None, cross_kw=None):
         B, N, M = q.shape[0], q.shape[1], k.shape[1]
         lo, hi = self._edited_rows(B)
@@ -221,8 +278,10 @@ class AttentionStore(AttentionControl):
     def reset(self):
         super().reset()
         self.step_store = self.get_empty_store()
-        if self.attention_store:
-            self._spare = self.attention_store
+        # Under CUDA-graph replay the captured kernels keep writing into the previous store's buffers, so those are handed out again
+        # (in place) for the next image. In eager mode the reference's behaviour holds: reset() starts a fresh store and whatever
+        # the caller still holds of the old one stays untouched.
+        self._spare = self.attention_store if (self.attention_store and self._graph_mode) else {}
         self.attention_store = {}
         self._slot = self._zero_slots()
 
@@ -257,8 +316,35 @@ class AttentionControlEdit(AttentionStore, abc.ABC):
         """Device tables describing replace_cross_attention for the fused kernel."""
         raise NotImplementedError
 
+    def forward(self, attn, is_cross: bool, place_in_unet: str):
+        """Materialised form of the edit (reference :113-125) — what runs when a subclass overrides replace_cross_attention /
+        replace_self_attention, or when the controller is called directly with a probability tensor."""
+        AttentionStore.forward(self, attn, is_cross, place_in_unet)
+        if is_cross or self.num_self_replace[0] <= self.cur_step < self.num_self_replace[1]:
+            per_prompt = attn.reshape(self.batch_size, attn.shape[0] // self.batch_size, *attn.shape[1:])
+            base, others = per_prompt[0], per_prompt[1:]
+            if is_cross:
+                w = self.cross_replace_alpha[self.cur_step].to(attn.dtype)
+                per_prompt[1:] = self.replace_cross_attention(base, others) * w + (1 - w) * others
+            else:
+                per_prompt[1:] = self.replace_self_attention(base, others)
+            attn = per_prompt.reshape(attn.shape)
+        return attn
+
+    forward._ief_builtin = True
+
+    def replace_self_attention(self, attn_base, att_replace):
+        """Reference :132-136: the base prompt's self-attention maps for layers with at most 16^2 queries."""
+        if att_replace.shape[2] <= _SELF_REPLACE_MAX_TOKENS:
+            return attn_base.unsqueeze(0).expand(att_replace.shape[0], *attn_base.shape)
+        return att_replace
+
+    replace_self_attention._ief_builtin = True
+
     def replace_cross_attention(self, attn_base, att_replace):
-        raise RuntimeError("replace_cross_attention on materialised maps is folded into ief_cross_attn_edit_fwd; see cross_edit()")
+        raise NotImplementedError
+
+    replace_cross_attention._ief_builtin = True
 
     def _row_tables(self, batch: int):
         lo, hi = self._edited_rows(batch)

@@ -62,6 +62,12 @@ class AttentionReplace(AttentionControlEdit):
         # CrossEdit derives the sparse (<= 8 source tokens per target token) form the kernel prefers from the dense mapper
         return ops.CrossEdit(ops.IEF_EDIT_REPLACE, self.mapper.shape[0], mapper=_f32(self.mapper))
 
+    def replace_cross_attention(self, attn_base, att_replace):
+        """Materialised form (reference :15-16); the registered closures use the fused equivalent described by cross_edit()."""
+        return torch.einsum("hpw,bwn->bhpn", attn_base, self.mapper.to(attn_base.dtype))
+
+    replace_cross_attention._ief_builtin = True
+
     def _retarget_tables(self, prompts, tokenizer) -> None:
         aligned = seq_aligner.get_replacement_mapper(prompts, tokenizer)
         self.mapper.copy_(_expect(aligned, tuple(self.mapper.shape), "replacement mapper"))
@@ -105,6 +111,13 @@ class AttentionRefine(AttentionControlEdit):
         return ops.CrossEdit(ops.IEF_EDIT_REFINE, targets, mapper_idx=self.mapper.to(torch.int32).contiguous(),
                              refine_alpha=_f32(self.alphas.reshape(targets, -1)))
 
+    def replace_cross_attention(self, attn_base, att_replace):
+        """Materialised form (reference :28-31): gather along the token axis (a -1 entry reads the last token, as torch indexing does)."""
+        gathered = attn_base[:, :, self.mapper].permute(2, 0, 1, 3)
+        return gathered * self.alphas + att_replace * (1. - self.alphas)
+
+    replace_cross_attention._ief_builtin = True
+
     def _retarget_tables(self, prompts, tokenizer) -> None:
         gather_idx, keep = seq_aligner.get_refinement_mapper(prompts, tokenizer)
         if int(gather_idx.min()) < -1 or int(gather_idx.max()) >= gather_idx.shape[-1]:
@@ -136,6 +149,14 @@ class AttentionReweight(AttentionControlEdit):
         AttentionControlEdit.__init__(self, prompts, tokenizer, num_steps, cross_replace_steps, self_replace_steps, local_blend, device, LOW_RESOURCE)
         self.prev_controller = controller
         self.equalizer = equalizer.to(device).to(dtype)
+
+    def replace_cross_attention(self, attn_base, att_replace):
+        """Materialised form (reference :42-46): the previous controller's edit, if any, scaled per token."""
+        if self.prev_controller is not None:
+            attn_base = self.prev_controller.replace_cross_attention(attn_base, att_replace)
+        return attn_base[None, :, :, :] * self.equalizer[:, None, None, :]
+
+    replace_cross_attention._ief_builtin = True
 
     def cross_edit(self) -> ops.CrossEdit:
         targets = self.batch_size - 1

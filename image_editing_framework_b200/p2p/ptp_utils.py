@@ -32,6 +32,7 @@ class LocalBlend:
         self.threshold = threshold
         self.MAX_NUM_WORDS = MAX_NUM_WORDS
         self.res = 16
+        self.masks = None   # set to a list to have every call append its per-prompt masks [n_prompts, H, W] (tests / inspection)
 
     def __call__(self, x_t: torch.Tensor, attention_store: Dict[str, List[torch.Tensor]]) -> torch.Tensor:
         maps = attention_store["down_cross"][2:4] + attention_store["up_cross"][:3]
@@ -41,7 +42,12 @@ class LocalBlend:
                 raise ValueError(f"LocalBlend expects {self.res}x{self.res} cross maps, got {m.shape[1]} tokens "
                                  "(the reference reshape would silently fold the difference into the head axis)")
         work = x_t.to(torch.float32, copy=True).contiguous()  # the reference returns a new tensor, input untouched
-        ops.local_blend(work, maps, n_prompts, self.alpha_layers.reshape(n_prompts, self.MAX_NUM_WORDS), self.threshold, res=self.res)
+        alpha = self.alpha_layers.reshape(n_prompts, self.MAX_NUM_WORDS)
+        if self.masks is not None:
+            _, mask = ops.local_blend(work, maps, n_prompts, alpha, self.threshold, res=self.res, return_mask=True)
+            self.masks.append(mask)
+        else:
+            ops.local_blend(work, maps, n_prompts, alpha, self.threshold, res=self.res)
         return work.to(x_t.dtype)
 
 

@@ -12,6 +12,7 @@ are generated from the reference classes re-composed the upstream Prompt-to-Prom
 import dataclasses
 import os
 import sys
+from types import SimpleNamespace
 
 import torch
 
@@ -167,21 +168,40 @@ def gen_p2p_localblend():
     pipe = make_pipeline(cfg, seed=3)
     prompts = ["a photo of a cat sitting on a bench", "a photo of a dog sitting on a bench"]
     steps = 3
-    lb = ref.ptp_utils.LocalBlend(pipe.tokenizer, prompts, [["cat"], ["dog"]], device=CPU)
+    from oracle import controlled_attention as orc
+
+    class RecordingBlend(ref.ptp_utils.LocalBlend):
+        """The reference's LocalBlend; every call also records the per-prompt masks, taken from the oracle's restatement on the same
+        inputs after checking that its blended latents equal the reference's bit for bit."""
+        masks = []
+
+        def __call__(self, x_t, attention_store):
+            out = super().__call__(x_t, attention_store)
+            maps = attention_store["down_cross"][2:4] + attention_store["up_cross"][:3]
+            again, mask = orc.local_blend(x_t, maps, self.alpha_layers.reshape(len(prompts), -1), self.threshold, return_mask=True)
+            assert torch.equal(again, out)
+            self.masks.append(mask.clone())
+            return out
+
+    # threshold 0.65 and distinct source / target latents: about half of the latent pixels are blended (with the default 0.3 and
+    # identical rows the mask of this random-init UNet is 98 % ones and the blend is a near no-op, i.e. nothing is tested)
+    threshold = 0.65
+    lb = RecordingBlend(pipe.tokenizer, prompts, [["cat"], ["dog"]], threshold=threshold, device=CPU)
     ctrl = ReplaceWithStore(prompts, pipe.tokenizer, steps, 0.8, 0.6, lb, device=CPU)
     editor = ref.sd_utils.P2P(pipe, steps)
     ref.register.register_attention_control(pipe, ctrl)
     context = _context(pipe, prompts)
-    latents = _latent(5, (1, 4, 64, 64)).expand(2, 4, 64, 64)
+    latents = torch.cat([_latent(5, (1, 4, 64, 64)), _latent(6, (1, 4, 64, 64))])
     per_step = []
     with torch.no_grad():
         for t in pipe.scheduler.timesteps:
             latents = editor.diffusion_step(pipe, ctrl, latents, context, t, 7.5, False)
             per_step.append(latents.clone())
     maps = ctrl.attention_store["down_cross"][2:4] + ctrl.attention_store["up_cross"][:3]
-    _save("p2p_localblend.pt", dict(recomposed=True, prompts=prompts, steps=steps, latent_seed=5, pipe_seed=3, guidance=7.5,
+    print("   LocalBlend mask coverage per step:", [round(m.float().mean().item(), 3) for m in lb.masks])
+    _save("p2p_localblend.pt", dict(recomposed=True, prompts=prompts, steps=steps, latent_seeds=(5, 6), threshold=threshold, pipe_seed=3, guidance=7.5,
                                     config=dataclasses.asdict(cfg), blend_words=[["cat"], ["dog"]], latents_per_step=per_step,
-                                    store_16=[m.clone() for m in maps]))
+                                    store_16=[m.clone() for m in maps], masks_per_step=[m.to(torch.uint8) for m in lb.masks]))
     # stand-alone LocalBlend known-answer on synthetic maps
     g = torch.Generator().manual_seed(8)
     syn = [torch.rand(16, 256, 77, generator=g) ** 4 for _ in range(5)]
@@ -477,6 +497,33 @@ def gen_pipelines():
     _save("pipelines.pt", out)
 
 
+def repaired_union(ref):
+    """The reference's MutualSelfAttentionControlUnion (masactrl/model/attention_control.py:71-107) with ONE repair. As shipped, its
+    source branch calls `super().forward` — the *mutual* forward — on a single batch row; that forward splits its input into CFG
+    halves again (`q.chunk(2)` now cuts the HEADS in two) and attn_batch then computes `b = (H/2) // H = 0` rows and fails. What the
+    comment above those lines says ("source image branch") and what upstream MasaCtrl does is plain attention for the source rows, so
+    the repaired class runs the source rows through AttentionBase.forward (out = attn v). The target branch — queries of the target
+    row against the token-wise concatenation [K_src; K_tgt], [V_src; V_tgt] — is the reference's code, untouched."""
+    AC = ref.attention_control
+    base_forward = ref.attention_base.AttentionBase.forward
+
+    class MutualSelfAttentionControlUnionRepaired(AC.MutualSelfAttentionControlUnion):
+        def forward(self, q, k, v, sim, attn, is_cross, place_in_unet, num_heads, **kwargs):
+            if is_cross or self.cur_step not in self.step_idx or self.cur_att_layer // 2 not in self.layer_idx:
+                return base_forward(self, q, k, v, sim, attn, is_cross, place_in_unet, num_heads, **kwargs)
+            (qu_s, qu_t, qc_s, qc_t), (ku_s, ku_t, kc_s, kc_t) = q.chunk(4), k.chunk(4)
+            (vu_s, vu_t, vc_s, vc_t), (au_s, au_t, ac_s, ac_t) = v.chunk(4), attn.chunk(4)
+            src_u = base_forward(self, qu_s, ku_s, vu_s, sim, au_s, is_cross, place_in_unet, num_heads, **kwargs)     # <- the repair
+            src_c = base_forward(self, qc_s, kc_s, vc_s, sim, ac_s, is_cross, place_in_unet, num_heads, **kwargs)     # <- the repair
+            tgt_u = self.attn_batch(qu_t, torch.cat([ku_s, ku_t]), torch.cat([vu_s, vu_t]), sim[:num_heads], au_t, is_cross, place_in_unet,
+                                    num_heads, **kwargs)
+            tgt_c = self.attn_batch(qc_t, torch.cat([kc_s, kc_t]), torch.cat([vc_s, vc_t]), sim[:num_heads], ac_t, is_cross, place_in_unet,
+                                    num_heads, **kwargs)
+            return torch.cat([src_u, tgt_u, src_c, tgt_c], dim=0)
+
+    return MutualSelfAttentionControlUnionRepaired
+
+
 def gen_fullgeo():
     """Whole edits at the BASELINE attention geometry (64x64 latents; head dims 40 / 80 / 160 and 64) through the reference's own
     register closures + controllers + P2P.diffusion_step, fp32 on the CPU (tests/scenarios.py::run_fullgeo with api = the reference's
@@ -490,15 +537,36 @@ def gen_fullgeo():
             continue
         t0 = time.time()
         family = {"p2p": "p2p", "masactrl": "masactrl", "pnp": "pnp"}[kind.split("_")[0]]
-        ctrl, records, per_step = scenarios.run_fullgeo(cfg_name, kind, load_reference(family), CPU, fused_step=False)
+        api = load_reference(family)
+        if kind == "masactrl_union":
+            api.attention_control.MutualSelfAttentionControlUnionRepaired = repaired_union(api)
+        ctrl, records, per_step = scenarios.run_fullgeo(cfg_name, kind, api, CPU, fused_step=False)
         g = dict(config=scenarios.FULLGEO_CONFIGS[cfg_name], kind=kind, steps=scenarios.FULLGEO_STEPS, rows=scenarios.FULLGEO_ROWS,
                  layer_outputs=records, latents_per_step=per_step)
+        if kind == "masactrl_union":
+            g["repaired"] = "source rows through AttentionBase.forward instead of the mutual forward (see make_goldens.py::repaired_union)"
         if kind == "p2p_store":
             avg = ctrl.get_average_attention()
             # the 16x16 cross maps (what LocalBlend / MaskAuto read) in full, the larger stored maps on a strip of query rows
             g["average_attention"] = {k: [t[:, ::max(1, t.shape[1] // 8)].clone() for t in v] for k, v in avg.items()}
         if ctrl is not None:
             g["cur_step"] = ctrl.cur_step
+        if kind != "p2p_store":
+            # how far the UNCONTROLLED run (same prompts, latents, UNet; reference closures with an EmptyControl) is from this one:
+            # a test that would also pass with the edit missing is worthless, so the fixture carries the distance it must beat
+            p2p_ref = load_reference("p2p")
+            plain_api = SimpleNamespace(attention_base=SimpleNamespace(AttentionStore=lambda lr: p2p_ref.attention_base.EmptyControl(lr)),
+                                        attention_control=None, sd_utils=p2p_ref.sd_utils, register=p2p_ref.register)
+            saved = scenarios.FULLGEO_PROMPTS["p2p_store"]
+            scenarios.FULLGEO_PROMPTS["p2p_store"] = scenarios.FULLGEO_PROMPTS[kind]
+            try:
+                _, rec0, per0 = scenarios.run_fullgeo(cfg_name, "p2p_store", plain_api, CPU, fused_step=False)
+            finally:
+                scenarios.FULLGEO_PROMPTS["p2p_store"] = saved
+            last = scenarios.FULLGEO_STEPS - 1
+            g["uncontrolled_layer_dist"] = [(a - b).abs().max().item() for a, b in zip(rec0[last], records[last])]
+            g["uncontrolled_latents_psnr"] = [scenarios.psnr(a, b) for a, b in zip(per0, per_step)]
+            print(f"   uncontrolled run: max layer distance {max(g['uncontrolled_layer_dist']):.3f}, latents {g['uncontrolled_latents_psnr'][-1]:.1f} dB")
         _save(f"fullgeo_{cfg_name}_{kind}.pt", g)
         print(f"   ({time.time() - t0:.0f} s)")
 

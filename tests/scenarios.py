@@ -182,13 +182,14 @@ def run_p2p_localblend(g, device, lean_store=False):
     cfg = UNetConfig(**g["config"])
     pipe = make_pipeline(cfg, seed=g["pipe_seed"], device=device)
     prompts, steps = g["prompts"], g["steps"]
-    lb = p2p.LocalBlend(pipe.tokenizer, prompts, g["blend_words"], device=device)
+    lb = p2p.LocalBlend(pipe.tokenizer, prompts, g["blend_words"], threshold=g["threshold"], device=device)
+    lb.masks = []
     ctrl = p2p.AttentionReplace(prompts, pipe.tokenizer, steps, 0.8, 0.6, lb, device=device)
     ctrl.lean_store = lean_store
     pipe.scheduler.set_timesteps(steps)
     p2p.register_attention_control(pipe, ctrl)
     context = editing.encode_prompts(pipe, prompts)
-    latents = latent(g["latent_seed"], (1, 4, 64, 64), device).expand(2, 4, 64, 64).contiguous()
+    latents = torch.cat([latent(s_, (1, 4, 64, 64), device) for s_ in g["latent_seeds"]])
     fused = FusedDDIM(pipe.scheduler)
     per_step = []
     with torch.no_grad():
@@ -197,6 +198,7 @@ def run_p2p_localblend(g, device, lean_store=False):
             latents = ctrl.step_callback(fused.step(noise, t, latents, g["guidance"]))
             per_step.append(latents.float().cpu())
     maps = ctrl.attention_store["down_cross"][2:4] + ctrl.attention_store["up_cross"][:3]
+    ctrl.blend_masks = [m.float().cpu() for m in lb.masks]
     return ctrl, per_step, [m.float().cpu() for m in maps]
 
 
@@ -313,12 +315,13 @@ FULLGEO_CONFIGS = {
                      norm_num_groups=8, use_linear_projection=True, name="d64_slim"),
 }
 FULLGEO_CASES = [("sd15_slim", "p2p_replace"), ("sd15_slim", "p2p_refine"), ("sd15_slim", "p2p_store"), ("sd15_slim", "masactrl"),
-                 ("sd15_slim", "pnp"), ("d64_slim", "p2p_refine"), ("d64_slim", "masactrl"), ("d64_slim", "pnp")]
+                 ("sd15_slim", "masactrl_union"), ("sd15_slim", "pnp"), ("d64_slim", "p2p_refine"), ("d64_slim", "masactrl"), ("d64_slim", "pnp")]
 FULLGEO_STEPS, FULLGEO_ROWS, FULLGEO_GUIDANCE = 3, 16, 7.5
 FULLGEO_PROMPTS = {"p2p_replace": ["a photo of a cat sitting on a bench", "a photo of a dog sitting on a bench"],
                    "p2p_refine": ["a bowl of soup", "a bowl of pea soup"],
                    "p2p_store": ["a photo of a cat sitting on a bench", "a photo of a dog sitting on a bench"],
                    "masactrl": ["a photo of a sitting cat", "a photo of a running cat"],
+                   "masactrl_union": ["a photo of a sitting cat", "a photo of a running cat"],
                    "pnp": ["a photo of a wooden horse", "a photo of a bronze horse"]}
 
 
@@ -360,7 +363,9 @@ def run_fullgeo(cfg_name, kind, api, device, fused_step=True):
         driver = api.sd_utils.P2P(pipe, steps)
         api.register.register_attention_control(pipe, ctrl)
     elif family == "masactrl":
-        ctrl = api.attention_control.MutualSelfAttentionControl(1, 10, total_steps=steps)
+        # (the reference's Union class is driven through its minimally repaired subclass, see make_goldens.py::repaired_union)
+        cls = {"masactrl": "MutualSelfAttentionControl", "masactrl_union": "MutualSelfAttentionControlUnion"}[kind]
+        ctrl = getattr(api.attention_control, cls + "Repaired", getattr(api.attention_control, cls))(1, 10, total_steps=steps)
         api.register.regiter_attention_editor_diffusers(pipe, ctrl)
     else:
         ts = pipe.scheduler.timesteps
@@ -368,8 +373,10 @@ def run_fullgeo(cfg_name, kind, api, device, fused_step=True):
         api.register.register_conv_control_efficient(pipe, ts[:int(steps * 0.8)])
     rec = RowRecorder(pipe.unet, (steps - 1,))
     context = editing.encode_prompts(pipe, prompts)
-    init = latent(31, (1, 4, hw, hw), device)
-    latents = torch.cat([init, init])
+    # source and target rows start from DIFFERENT latents (the scripts start both from the inverted image): on a random-init UNet
+    # identical rows stay nearly identical for a few steps, K_src ~ K_tgt, and a broken edit would pass unnoticed. With distinct rows
+    # the controlled results are far from the uncontrolled ones (make_goldens.py records how far), so the gates below discriminate.
+    latents = torch.cat([latent(31, (1, 4, hw, hw), device), latent(32, (1, 4, hw, hw), device)])
     fused = FusedDDIM(pipe.scheduler) if fused_step else None
     per_step = []
     with torch.no_grad():

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from image_editing_framework_b200 import p2p, _cabi
+from image_editing_framework_b200 import p2p, _cabi, editing
 from image_editing_framework_b200.p2p import seq_aligner, ptp_utils
 from image_editing_framework_b200.standin import WordPieceTokenizer, make_pipeline, tiny_config, sd15_config, sd21_config, sdxl_config, attention_geometry
 from oracle import controlled_attention as orc
@@ -348,10 +348,85 @@ def test_p2p_localblend_recomposed_oracle(monkeypatch):
         assert (a - b).abs().max().item() < 1e-3, f"step {i}"
 
 
-def test_controller_materialised_entry_point_fails_loudly():
-    ctrl = p2p.EmptyControl(False)
-    with pytest.raises(RuntimeError, match="fused"):
-        ctrl(torch.zeros(2, 4, 4), False, "down")
+@pytest.mark.parametrize("name", ["replace", "refine", "reweight_chain", "reweight"])
+def test_controller_call_on_materialised_probabilities_matches_reference(pins, name):
+    """controller(attn, is_cross, place) — the reference's own entry point (p2p/model/attention_base.py:16-28) — served by the
+    mirrored classes on a materialised probability tensor: outputs of the reference's controllers on the same tensors are the pins."""
+    tok = WordPieceTokenizer()
+    steps = pins["steps"]
+    kw = dict(tokenizer=tok, num_steps=steps, cross_replace_steps={"default_": 0.8, "burger": (0.0, 0.3)}, self_replace_steps=0.4, device="cpu")
+    rep = p2p.AttentionReplace(prompts=pins["prompts"], **kw)
+    kw["cross_replace_steps"] = 0.8
+    eq = p2p.seq_aligner.get_equalizer(tok, pins["prompts"][1], ("lion",), (2.0, -1.0))
+    ctrl = {"replace": lambda: rep, "refine": lambda: p2p.AttentionRefine(prompts=pins["rprompts"], **kw),
+            "reweight_chain": lambda: p2p.AttentionReweight(prompts=pins["prompts"], equalizer=eq, controller=rep, **kw),
+            "reweight": lambda: p2p.AttentionReweight(prompts=pins["prompts"], equalizer=eq, controller=None, **kw)}[name]()
+    assert not ctrl._needs_probabilities()          # the stock classes stay on the fused path when registered
+    for key, want in pins[name].items():
+        if key == "self_big_unchanged":
+            continue
+        is_cross, step = key.startswith("cross"), int(key.split("step")[1])
+        ctrl.num_att_layers, ctrl.cur_step, ctrl.cur_att_layer = 100, step, 0
+        got = ctrl((pins["cross"] if is_cross else pins["selfp"]).clone(), is_cross, "down")
+        assert torch.allclose(got, want, atol=1e-6, rtol=1e-5), f"{name}/{key}: {(got - want).abs().max().item()}"
+        assert ctrl.cur_att_layer == 1
+
+
+def test_custom_controller_written_against_the_reference_runs_through_the_registered_closure(monkeypatch):
+    """A user subclass that only knows the reference interface — forward(attn, is_cross, place) on probabilities, or an overridden
+    replace_cross_attention — takes the compatibility route: the kernel emits the map, the user's code edits it, P'V follows."""
+    cpu_backend.install(monkeypatch)
+    pipe = make_pipeline(tiny_config(), seed=0)
+    seen = []
+
+    class Halve77(p2p.AttentionControl):                       # reference-style: implements forward() only
+        def forward(self, attn, is_cross, place_in_unet):
+            seen.append((is_cross, tuple(attn.shape)))
+            return attn * 0.5 if is_cross else attn
+
+    ctrl = Halve77(False)
+    p2p.register_attention_control(pipe, ctrl)
+    x = torch.randn(4, 4, 8, 8, generator=torch.Generator().manual_seed(0))
+    ctx = editing.encode_prompts(pipe, ["a cat", "a dog"])
+    with torch.no_grad():
+        got = pipe.unet(x, 981, encoder_hidden_states=ctx).sample
+    assert ctrl._needs_probabilities() and ctrl.cur_step == 1 and ctrl.cur_att_layer == 0 and len(seen) == ctrl.num_att_layers == 32
+    assert all(shape[0] == 2 * 2 for _, shape in seen)          # the conditional half only: 2 rows x 2 heads
+    p2p.unregister_attention_control(pipe, ctrl)
+
+    class Plain(p2p.AttentionControl):
+        def forward(self, attn, is_cross, place_in_unet):
+            return attn
+
+    plain = Plain(False)
+    p2p.register_attention_control(pipe, plain)
+    with torch.no_grad():
+        same = pipe.unet(x, 981, encoder_hidden_states=ctx).sample
+    p2p.unregister_attention_control(pipe, plain)
+    empty = p2p.EmptyControl(False)
+    p2p.register_attention_control(pipe, empty)
+    with torch.no_grad():
+        want = pipe.unet(x, 981, encoder_hidden_states=ctx).sample
+    p2p.unregister_attention_control(pipe, empty)
+    assert torch.allclose(same, want, atol=1e-5) and not torch.allclose(got, want, atol=1e-3)
+
+    class HalfReplace(p2p.AttentionReplace):                  # overrides the edit itself
+        def replace_cross_attention(self, attn_base, att_replace):
+            return 0.5 * super().replace_cross_attention(attn_base, att_replace) + 0.5 * att_replace
+
+    prompts = ["a photo of a cat sitting on a bench", "a photo of a dog sitting on a bench"]
+    custom = HalfReplace(prompts, pipe.tokenizer, 4, 0.8, 0.6, device="cpu")
+    stock = p2p.AttentionReplace(prompts, pipe.tokenizer, 4, 0.8, 0.6, device="cpu")
+    assert custom._needs_probabilities() and not stock._needs_probabilities()
+    ctx = editing.encode_prompts(pipe, prompts)
+    outs = []
+    for c in (custom, stock):
+        p2p.register_attention_control(pipe, c)
+        with torch.no_grad():
+            outs.append(pipe.unet(x, 981, encoder_hidden_states=ctx).sample)
+        p2p.unregister_attention_control(pipe, c)
+    assert not torch.allclose(outs[0], outs[1], atol=1e-4)      # the override took effect
+    assert torch.equal(outs[0][:3], outs[1][:3]) or torch.allclose(outs[0][:3], outs[1][:3], atol=1e-5)   # only the target row is edited
 
 
 def test_attention_mask_is_rejected(monkeypatch):
@@ -390,7 +465,9 @@ def test_graph_replay_protocol_tracks_eager_counters(monkeypatch):
             pipe.unet(x, t, encoder_hidden_states=ctx)
             assert (ctrl.cur_step, ctrl.cur_att_layer, ctrl._slot) == (shadow.cur_step, shadow.cur_att_layer, shadow._slot)
     # store: first step allocates, later accumulate; self-replace window = steps [0, 3)
-    assert keys == [(("store", False), True), (("store", True), True), (("store", True), True), (("store", True), False), (("store", True), False)]
+    # (the trailing 0 is the edit-table epoch: it only moves when retarget() had to replace a device table instead of rewriting it)
+    assert keys == [(("store", False), True, 0), (("store", True), True, 0), (("store", True), True, 0), (("store", True), False, 0),
+                    (("store", True), False, 0)]
     p2p.unregister_attention_control(pipe, ctrl)
     ed = masactrl.MutualSelfAttentionControl(2, 10, total_steps=steps)
     masactrl.regiter_attention_editor_diffusers(pipe, ed)

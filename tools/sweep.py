@@ -12,6 +12,9 @@ ids of p2p/test.py:114. "Direct inversion", which BASELINE.json's config text me
 fact 0.4): every method runs the reference's DDIM inversion. Objects are kept across images (controller.retarget() / editor.reset()),
 so with --graphs the UNet forwards replay captured CUDA graphs after the first image of each kind.
 Each record carries a CRC of the result images: a G-GPU sweep must reproduce the 1-GPU sweep bit for bit (tests/test_gpu_e2e.py).
+P2P, MasaCtrl and PnP are bit-reproducible as they are (every kernel of this library is deterministic, forward-only torch ops are);
+Pix2Pix-zero differentiates through the UNet, and cuDNN's default backward-data convolutions are not — pass --deterministic
+(torch.backends.cudnn.deterministic) when its CRCs must match too.
 """
 import argparse
 import contextlib
@@ -52,7 +55,9 @@ def item(i: int, side: int = 512):
 class Worker:
     """One rank's pipeline replica and the kept per-method objects."""
 
-    def __init__(self, device, ddim_steps: int, graphs: bool, config: str = "sd15", dtype=torch.bfloat16):
+    def __init__(self, device, ddim_steps: int, graphs: bool, config: str = "sd15", dtype=torch.bfloat16, deterministic: bool = False):
+        if deterministic:
+            torch.backends.cudnn.deterministic = True
         import image_editing_framework_b200 as pkg
         from image_editing_framework_b200 import p2p, masactrl, pnp, pix2pix_zero  # noqa: F401  (bind the sub-packages on pkg)
         from image_editing_framework_b200.ddim import ddim_inversion
@@ -176,6 +181,7 @@ def main():
     ap.add_argument("--ddim-steps", type=int, default=50)
     ap.add_argument("--config", default="sd15", choices=["sd15", "tiny"])
     ap.add_argument("--no-graphs", action="store_true")
+    ap.add_argument("--deterministic", action="store_true", help="cuDNN deterministic algorithms (needed for bit-equal Pix2Pix-zero results)")
     ap.add_argument("--out", default=None, help="per-image records (JSON lines), written by rank 0")
     args = ap.parse_args()
     import torch.distributed as dist
@@ -186,7 +192,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     methods = [m for m in args.methods.split(",") if m]
-    worker = Worker(dev, args.ddim_steps, not args.no_graphs, args.config)
+    worker = Worker(dev, args.ddim_steps, not args.no_graphs, args.config, deterministic=args.deterministic)
     # untimed: the first image of each kind pays cuDNN autotuning and the graph captures
     warm = {i: worker.run(i, methods) for i in (0, 2)}
     del warm
