@@ -246,7 +246,7 @@ int launch_dp(const MmaArgs& a, dim3 grid, cudaStream_t st) {
 // Probabilities only, from a known row log-sum-exp (log2 units): P = exp2(scale_log2 * Q K^T - lse). One sweep over the keys, no V,
 // no running statistics: used behind the tcgen05 kernels, which produce O and the lse, so that stored maps cost one QK^T on
 // mma.sync plus the HBM traffic of the maps instead of the two-sweep kernel above.
-template <int DTYPE, int DP>
+template <int DTYPE, int DP, bool ACCUM>
 __global__ void __launch_bounds__(kThreads)
 attn_probs_from_lse_kernel(const __grid_constant__ MmaArgs a, const float* __restrict__ lse, int nqt, int ksplit) {
   using E = ElemT<DTYPE>;
@@ -308,8 +308,36 @@ attn_probs_from_lse_kernel(const __grid_constant__ MmaArgs a, const float* __res
     }
     const int vc = min(kBN, a.Nk - jj * kBN);
     const int col0 = (blk2 ? a.Nk : 0) + jj * kBN;
+    if (vc == kBN && ((nk_total | col0) & 1) == 0) {
+      // Full tile, 8-byte aligned pairs. Accumulating: ALL sixteen old pairs of this thread are requested before the first store —
+      // written as load / add / store per pair, every load had to wait behind the previous store to the same array (they may alias
+      // as far as the compiler knows), i.e. sixteen serial DRAM round trips per tile: that chain, not bandwidth, bounded the sweep.
+      float2* d0 = reinterpret_cast<float2*>(a.probs + (prow + grow0) * nk_total + col0 + 2 * t);
+      float2* d1 = reinterpret_cast<float2*>(a.probs + (prow + grow0 + 8) * nk_total + col0 + 2 * t);
+      const bool r0 = grow0 < a.Nq, r1 = grow0 + 8 < a.Nq;
+      float2 o0[8], o1[8];
+      if constexpr (ACCUM) {
 #pragma unroll
-    for (int nb = 0; nb < 8; ++nb) {
+        for (int nb = 0; nb < 8; ++nb) {
+          o0[nb] = r0 ? d0[nb * 4] : make_float2(0.f, 0.f);
+          o1[nb] = r1 ? d1[nb * 4] : make_float2(0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb) {
+        float2 p0 = make_float2(ief_exp2(fmaf(s[nb][0], c2, -lse0)), ief_exp2(fmaf(s[nb][1], c2, -lse0)));
+        float2 p1 = make_float2(ief_exp2(fmaf(s[nb][2], c2, -lse1)), ief_exp2(fmaf(s[nb][3], c2, -lse1)));
+        if constexpr (ACCUM) {
+          p0.x += o0[nb].x; p0.y += o0[nb].y;
+          p1.x += o1[nb].x; p1.y += o1[nb].y;
+        }
+        if (r0) d0[nb * 4] = p0;
+        if (r1) d1[nb * 4] = p1;
+      }
+      continue;
+    }
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {   // ragged last tile / odd key counts: element-wise
       const int c = nb * 8 + 2 * t;
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
@@ -318,28 +346,18 @@ attn_probs_from_lse_kernel(const __grid_constant__ MmaArgs a, const float* __res
           const float ls = hh ? lse1 : lse0;
           float* dst = a.probs + (prow + r) * nk_total + col0 + c;
           const float p0 = ief_exp2(fmaf(s[nb][2 * hh], c2, -ls)), p1 = ief_exp2(fmaf(s[nb][2 * hh + 1], c2, -ls));
-          if (c + 1 < vc) {  // the pair as one 8-byte access (rows are 8-byte aligned when the key count is even)
-            if (((nk_total | col0) & 1) == 0) {  // (second key block of an odd key count starts on an odd column)
-              float2* d2 = reinterpret_cast<float2*>(dst);
-              float2 old = a.probs_accum ? *d2 : make_float2(0.f, 0.f);
-              *d2 = make_float2(old.x + p0, old.y + p1);
-            } else {
-              dst[0] = a.probs_accum ? dst[0] + p0 : p0;
-              dst[1] = a.probs_accum ? dst[1] + p1 : p1;
-            }
-          } else if (c < vc) {
-            dst[0] = a.probs_accum ? dst[0] + p0 : p0;
-          }
+          if (c < vc) dst[0] = ACCUM ? dst[0] + p0 : p0;
+          if (c + 1 < vc) dst[1] = ACCUM ? dst[1] + p1 : p1;
         }
       }
     }
   }
 }
 
-template <int DTYPE, int DP>
+template <int DTYPE, int DP, bool ACCUM>
 int launch_probs_one(const MmaArgs& a, const float* lse, dim3 grid, cudaStream_t st) {
   constexpr int smem = (kBM + 2 * kBN) * (DP + 8) * 2;
-  auto kern = attn_probs_from_lse_kernel<DTYPE, DP>;
+  auto kern = attn_probs_from_lse_kernel<DTYPE, DP, ACCUM>;
   IEF_CONFIG_SMEM(kern, smem);
   // enough CTAs for ~6 per SM: split the key range when the (row, head, query tile) grid alone is too small
   int stored_rows = 0;
@@ -354,15 +372,20 @@ int launch_probs_one(const MmaArgs& a, const float* lse, dim3 grid, cudaStream_t
   return IEF_OK;
 }
 
+template <int DTYPE, bool ACCUM>
+int launch_probs_dp2(const MmaArgs& a, const float* lse, dim3 grid, cudaStream_t st) {
+  const int d = a.d;
+  if (d <= 32) return launch_probs_one<DTYPE, 32, ACCUM>(a, lse, grid, st);
+  if (d <= 48) return launch_probs_one<DTYPE, 48, ACCUM>(a, lse, grid, st);
+  if (d <= 64) return launch_probs_one<DTYPE, 64, ACCUM>(a, lse, grid, st);
+  if (d <= 80) return launch_probs_one<DTYPE, 80, ACCUM>(a, lse, grid, st);
+  if (d <= 96) return launch_probs_one<DTYPE, 96, ACCUM>(a, lse, grid, st);
+  return launch_probs_one<DTYPE, 128, ACCUM>(a, lse, grid, st);
+}
+
 template <int DTYPE>
 int launch_probs_dp(const MmaArgs& a, const float* lse, dim3 grid, cudaStream_t st) {
-  const int d = a.d;
-  if (d <= 32) return launch_probs_one<DTYPE, 32>(a, lse, grid, st);
-  if (d <= 48) return launch_probs_one<DTYPE, 48>(a, lse, grid, st);
-  if (d <= 64) return launch_probs_one<DTYPE, 64>(a, lse, grid, st);
-  if (d <= 80) return launch_probs_one<DTYPE, 80>(a, lse, grid, st);
-  if (d <= 96) return launch_probs_one<DTYPE, 96>(a, lse, grid, st);
-  return launch_probs_one<DTYPE, 128>(a, lse, grid, st);
+  return a.probs_accum ? launch_probs_dp2<DTYPE, true>(a, lse, grid, st) : launch_probs_dp2<DTYPE, false>(a, lse, grid, st);
 }
 
 }  // namespace

@@ -112,15 +112,17 @@ def run_masactrl_masks(g, device, which):
     masactrl.regiter_attention_editor_diffusers(pipe, ctrl)
     context = editing.encode_prompts(pipe, g["prompts"])
     hw = g["latent_hw"]
-    init = latent(g["latent_seed"], (1, 4, hw, hw), device)
-    latents = torch.cat([init, init])
+    latents = torch.cat([latent(g["latent_seed"], (1, 4, hw, hw), device), latent(g["latent_seed"] + 1, (1, 4, hw, hw), device)])
     fused = FusedDDIM(pipe.scheduler)
+    rec = RowRecorder(pipe.unet, (steps - 1,))
     per_step = []
     with torch.no_grad():
-        for t in pipe.scheduler.timesteps.tolist():
+        for i, t in enumerate(pipe.scheduler.timesteps.tolist()):
+            rec.step = i
             noise = pipe.unet(torch.cat([latents] * 2), t, encoder_hidden_states=context).sample
             latents = fused.step(noise, t, latents, g["guidance"])
             per_step.append(latents.float().cpu())
+    ctrl.layer_rows = rec.records[steps - 1]
     return ctrl, per_step
 
 

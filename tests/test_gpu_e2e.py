@@ -59,12 +59,28 @@ def test_masactrl_edit_matches_reference(cuda):
 
 @pytest.mark.parametrize("which", ["mask", "mask_auto"])
 def test_masactrl_masked_variants_match_reference(cuda, which):
+    """MutualSelfAttentionControlMask / MaskAuto on distinct source / target rows: every attention layer's output of the last step
+    within 2e-2 of the reference's, where the same run with the masks ignored (plain mutual control) is 0.36 / 0.47 away (recorded in
+    the fixture), and the final latents within the 40 dB gate."""
     g = golden("masactrl_masks.pt")
-    _, per_step = scenarios.run_masactrl_masks(g, cuda, which)
+    ctrl, per_step = scenarios.run_masactrl_masks(g, cuda, which)
+    want = g[which + "_layers"][g["steps"] - 1]
+    assert len(ctrl.layer_rows) == len(want)
+    # MaskAuto derives its spatial mask by thresholding min-max normalised cross-attention maps: a query position whose map value sits
+    # near the threshold can land on the other side under bf16 (the normalisation amplifies the rounding of a flat map), and its
+    # whole output row then is the background instead of the foreground result, or vice versa. At most 2 of the 16 recorded
+    # positions of a layer, and at most 5 % of all recorded positions, may do so; the fixed-mask variant admits none.
+    flips_allowed = 2 if which == "mask_auto" else 0
+    off = total = 0
+    for i, (a, b) in enumerate(zip(ctrl.layer_rows, want)):
+        per_position = (a - b).abs().amax(dim=(0, 2))                 # [16 token rows]
+        bad = int((per_position >= LAYER_TOL).sum())
+        off, total = off + bad, total + per_position.numel()
+        assert bad <= flips_allowed, f"{which} layer {i}: {bad} of {per_position.numel()} positions off, worst {per_position.max().item():.4f}"
+    assert off <= 0.05 * total, f"{which}: {off} of {total} recorded positions off"
+    assert max(g[which + "_layer_dist_to_mutual"]) > 10 * LAYER_TOL, "fixture: the masks must matter"
     db = psnr(per_step[-1], g[which][-1])
     assert db >= PSNR_DB, f"{which}: final latents PSNR {db:.1f} dB"
-    # (on this random-init stand-in the masks move the latents by less than bf16 noise, so the discriminating checks are the
-    # fp32 host-logic test on the same golden and test_attn_key_bias_masked_masactrl / test_mask_blend at kernel level)
 
 
 def test_pnp_edit_matches_reference(cuda):
@@ -512,7 +528,8 @@ def test_edits_at_baseline_attention_geometry_match_reference(cuda, cfg_name, ki
         # the gates discriminate: the same run WITHOUT the control is far outside them (fixture property), and we are far closer to
         # the controlled reference than the uncontrolled run is
         assert max(g["uncontrolled_layer_dist"]) > 5 * LAYER_TOL
-        assert psnr(per_step[-1], g["latents_per_step"][-1]) >= g["uncontrolled_latents_psnr"][-1] + 6.0
+        if g["uncontrolled_latents_psnr"][-1] < 60.0:    # (above that the bf16 noise floor of ~73 dB leaves no room for a margin:
+            assert psnr(per_step[-1], g["latents_per_step"][-1]) >= g["uncontrolled_latents_psnr"][-1] + 6.0   # the per-layer gate decides)
     # the kernels that matter at this geometry really ran: tcgen05 for every self-attention layer with >= 1024 tokens (with the
     # probability sweep behind it where maps are stored), and for the plain cross-attention rows of the large layers
     big_self = [c for c in log.calls if c[0] == "self" and c[1] >= 1024]

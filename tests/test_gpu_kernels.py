@@ -584,3 +584,43 @@ def test_integration_md_stub_runs_the_kernel(cuda):
     assert _cabi.launch_count() > before
     want = orc.indexed_attention(q, k, v, H, d ** -0.5, k_src=src, v_src=src)
     assert (got.float().cpu() - want).abs().max().item() < TOL
+
+
+def test_two_devices_driven_from_two_threads_of_one_process():
+    """The library keeps no per-process launch state: per-device (kernel, device) configuration, the caller's stream, a thread-local
+    error string. cuda:0 first, then cuda:1 (the order that used to leave cuda:1 without its > 48 KB shared-memory opt-in), then both
+    concurrently from two threads, for a tcgen05 self-attention, an edited cross-attention and the mma.sync path each."""
+    import threading
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    B, H, N, d = 4, 8, 1024, 64
+    q, k, v = _qkv(B, N, N, H, d, 5)
+    kc, vc = (torch.randn(B, 77, H * d, generator=torch.Generator().manual_seed(9)).to(torch.bfloat16) for _ in range(2))
+    src = [0, 0, 2, 2]
+    want_self = orc.indexed_attention(q, k, v, H, d ** -0.5, k_src=src, v_src=src)
+    want_cross = orc.plain_attention(q, kc, vc, H, d ** -0.5)
+    errors = []
+
+    def work(index, rounds):
+        try:
+            dev = torch.device("cuda", index)
+            with torch.cuda.device(dev):
+                qd, kd, vd, kcd, vcd = (t.to(dev) for t in (q, k, v, kc, vc))
+                for _ in range(rounds):
+                    for impl in (ops.IEF_IMPL_TCGEN05, ops.IEF_IMPL_MMA):
+                        got = ops.attention(qd, kd, vd, H, d ** -0.5, k_src=src, v_src=src, impl=impl)
+                        assert (got.float().cpu() - want_self).abs().max().item() < TOL
+                    got = ops.cross_attention_edit(qd, kcd, vcd, H, d ** -0.5)
+                    assert (got.float().cpu() - want_cross).abs().max().item() < TOL
+        except Exception as e:   # noqa: BLE001 - reported to the main thread
+            errors.append((index, repr(e)))
+
+    work(0, 1)
+    work(1, 1)
+    assert not errors, errors
+    threads = [threading.Thread(target=work, args=(i, 5)) for i in (0, 1)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors

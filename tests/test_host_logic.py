@@ -293,6 +293,8 @@ def test_masactrl_masked_variants_reproduce_reference(monkeypatch, which):
     # the masks matter: plain mutual control on the same inputs ends somewhere else
     assert (g["mutual"][-1] - g[which][-1]).abs().max() > 50 * (per_step[-1] - g[which][-1]).abs().max()
     assert ctrl.cur_step == g["steps"]
+    for a, b in zip(ctrl.layer_rows, g[which + "_layers"][g["steps"] - 1]):
+        assert torch.allclose(a, b, atol=2e-4), (a - b).abs().max()
 
 
 def test_pnp_host_logic_reproduces_reference(monkeypatch):
