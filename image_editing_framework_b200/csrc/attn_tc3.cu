@@ -65,10 +65,15 @@ constexpr int kSmemXchg = 8 * 1024;            // floats: row-max exchange [2 pa
 #ifndef IEF_TC3_HANDOVER_LATE
 #define IEF_TC3_HANDOVER_LATE 0  // experiment: hand the turn over after the whole exp section instead of one chunk early
 #endif
+// Every IEF_TC3_EMUL-th column pair is exponentiated on the FMA / ALU pipes (Cody-Waite + degree-3 minimax, 7.5e-5, attn_tc_dev.cuh)
+// inside the exp section, interleaved with the MUFU ones. Round 1 measured no gain from this (and a loss when placed before the turn):
+// the kernel was then equally bound by the single MMA issuer's chain of round trips. With two issuers (kDualIssue) the exp pipe is
+// the binding unit and a quarter of the pairs on the FMA pipe buys +9-10 % at head_dim 40, +3 % at 64 (1/6: +8 / +1, 1/3: +6 / -1,
+// 1/2: +3 / -8 %; profiles/r02_attn_tc3_dual_issue_emulation.txt).
 #ifndef IEF_TC3_EMUL
-#define IEF_TC3_EMUL 0
+#define IEF_TC3_EMUL 4
 #endif
-constexpr int kDefaultEmul = IEF_TC3_EMUL;  // measured: 1/6 of the pairs = +-0 %, 1/4 and 1/3 = -4 % (the pre-turn latency chain, not the MUFU, is critical)
+constexpr int kDefaultEmul = IEF_TC3_EMUL;
 constexpr float kRescaleThreshold = 8.0f;
 // bf16 only: a tile whose Cauchy-Schwarz score bound stays within 2^kSkipMargin of the first tile's smallest row maximum needs no
 // row-maximum pass at all (P and the fp32 accumulators have 8 exponent bits; see the softmax section)
@@ -82,6 +87,14 @@ constexpr float kNoMaxLo = 7.8886090522101181e-31f, kNoMaxHi = 1.267650600228229
 #define IEF_TC3_FAST_SCALE_IN_TURN 0  // 1: the scale multiply rides inside the exp section instead of before the turn (A/B)
 #endif
 constexpr bool kFastOrdered = IEF_TC3_FAST_ORDERED != 0;
+// Two tcgen05.mma issuer warps, one per stream (warp 1: stream 0, warp 2: stream 1), instead of one warp walking QK_0 QK_1 PV_0 PV_1 in
+// a fixed order with a blocking wait before each: a commit group needs ~300 clk from issue to its barrier (tools/micro/umma_rate.cu) and
+// the softmax side reacts to each of them, so the single in-order issuer strung four such round trips together per key tile — ~2350 clk
+// per tile pair even with every exponential removed (profiles/r02_tc3_no_exp_diagnostic.txt), as much as the exp sections themselves.
+#ifndef IEF_TC3_DUAL_ISSUE
+#define IEF_TC3_DUAL_ISSUE 1
+#endif
+constexpr bool kDualIssue = IEF_TC3_DUAL_ISSUE != 0;
 
 // mbarrier phase-parity bases of a pass: zero for the first (or only) pass; for the exact second pass of a MAXMODE 2 CTA the number
 // of phases each barrier completed during the first pass, mod 2
@@ -194,9 +207,9 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     for (int s = 0; s < ST; ++s) {
       mbar_init(bar_kf(s), 1);
-      mbar_init(bar_ke(s), 1);
+      mbar_init(bar_ke(s), kDualIssue ? 2 : 1);
       mbar_init(bar_vf(s), 1);
-      mbar_init(bar_ve(s), 1);
+      mbar_init(bar_ve(s), kDualIssue ? 2 : 1);
     }
     *redo_flag = 0;
     fence_barrier_init();
@@ -257,7 +270,7 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   };
 
   // ------------------------------------------------------------------ MMA issuer (warp 1: whole warp waits, one elected lane issues)
-  auto mma_issuer = [&](auto pb) {
+  auto mma_issuer = [&](auto pb, int t_lo, int t_hi) {
     const uint64_t desc_k = make_smem_desc_sw128(0, 16, 1024);
     const uint64_t desc_v = make_smem_desc_sw128(0, kTcChunkBytes, 1024);
     auto issue_qk = [&](int t, int s) {
@@ -275,13 +288,20 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           umma_ts(tmem_base + 384 + 64 * t + a.dv_mma, tmem_base + 256 + 64 * t + k * 8, desc_k | ((sOnes + (k & 3) * 32) >> 4), a.idesc_sum, acc || (k > 0));
       }
     };
+    // This warp issues for the streams [t_lo, t_hi): both (one issuer) or one each (two issuers, kDualIssue). Every issuer arrives
+    // once per ring stage on the "K consumed" / "V consumed" barriers (their count = number of issuers), through a commit when it
+    // has MMAs in flight on that stage and through a plain arrive when its stream has no tile there.
+    auto release = [&](uint32_t bar, bool issued) {
+      if (issued) umma_commit(bar); else mbar_arrive(bar);
+    };
     mbar_wait(bar_q, 0);
     mbar_wait(bar_kf(0), pb.stage(0));
     tc_fence_after();
     if (elect_one()) {
-      issue_qk(0, 0);
-      if (nt1 > 0) issue_qk(1, 0);
-      umma_commit(bar_ke(0));
+      bool any = false;
+      for (int t = t_lo; t < t_hi; ++t)
+        if (stream_nt(t) > 0) { issue_qk(t, 0); any = true; }
+      release(bar_ke(0), any);
     }
     __syncwarp();
     for (int j = 0; j < nt0; ++j) {
@@ -289,21 +309,22 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int s1 = (j + 1) % ST, ph1 = (((j + 1) / ST) + pb.stage(s1)) & 1;
       if (j + 1 < nt0) {  // next score tiles first: they only need S_t(j) to be in the softmax registers
         mbar_wait(bar_kf(s1), ph1);
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
+        bool any = false;
+        for (int t = t_lo; t < t_hi; ++t) {
           if (j + 1 < stream_nt(t)) {
             mbar_wait(bar_c(t), (j + pb.strm(t)) & 1);
             tc_fence_after();
             if (elect_one()) issue_qk(t, s1);
             __syncwarp();
+            any = true;
           }
         }
-        if (elect_one()) umma_commit(bar_ke(s1));
+        if (elect_one()) release(bar_ke(s1), any);
         __syncwarp();
       }
       mbar_wait(bar_vf(s), ph);
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
+      bool any = false;
+      for (int t = t_lo; t < t_hi; ++t) {
         if (j < stream_nt(t)) {
           mbar_wait(bar_p(t), (j + pb.strm(t)) & 1);
           tc_fence_after();
@@ -312,9 +333,10 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             umma_commit(bar_o(t));
           }
           __syncwarp();
+          any = true;
         }
       }
-      if (elect_one()) umma_commit(bar_ve(s));
+      if (elect_one()) release(bar_ve(s), any);
       __syncwarp();
     }
   };
@@ -322,13 +344,15 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp < 4) {
     reg_dec<kRegsLow>();
     if (warp == 0) producer(PbZero{}, true);
-    else if (warp == 1) mma_issuer(PbZero{});
+    else if (warp == 1) mma_issuer(PbZero{}, 0, kDualIssue ? 1 : 2);
+    else if (warp == 2 && kDualIssue) mma_issuer(PbZero{}, 1, 2);
     if constexpr (NOMAX) {
       named_bar_sync(0, kThreads);  // the softmax warps have looked at the row sums of the unshifted pass
       if (*redo_flag) {
         const PbPass2 pb = pass2_bases();
         if (warp == 0) producer(pb, false);
-        else if (warp == 1) mma_issuer(pb);
+        else if (warp == 1) mma_issuer(pb, 0, kDualIssue ? 1 : 2);
+        else if (warp == 2 && kDualIssue) mma_issuer(pb, 1, 2);
       }
     }
   } else {

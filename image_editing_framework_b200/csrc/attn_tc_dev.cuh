@@ -92,8 +92,10 @@ __device__ __forceinline__ float2 exp2_fma(float2 t) {
   const float2 magic = make_float2(12582912.f, 12582912.f), nmagic = make_float2(-12582912.f, -12582912.f), mone = make_float2(-1.f, -1.f);
   const float2 c3 = make_float2(0.0551716685f, 0.0551716685f), c2 = make_float2(0.2426111251f, 0.2426111251f),
                c1 = make_float2(0.6932609677f, 0.6932609677f), c0 = make_float2(0.9999280572f, 0.9999280572f);
-  t.x = fmaxf(t.x, -126.f);  // masked (-inf) and far-away keys end up as 2^-126 ~ 0 instead of wrapping the exponent field
-  t.y = fmaxf(t.y, -126.f);
+  // masked (-inf) and far-away keys end up as 2^-126 ~ 0 instead of wrapping the exponent field; the upper clamp matters to the
+  // unshifted loop only (a score beyond 2^127 must blow the row sum up, not wrap, so that the exact second pass is taken)
+  t.x = fminf(fmaxf(t.x, -126.f), 127.f);
+  t.y = fminf(fmaxf(t.y, -126.f), 127.f);
   const float2 r = fadd2(t, magic);
   const float2 fi = fadd2(r, nmagic);
   const float2 f = ffma2(fi, mone, t);
@@ -112,8 +114,12 @@ template <int EVERY> __device__ __forceinline__ constexpr bool emul_pair(int pai
 #ifndef IEF_SCALAR_SCALE
 #define IEF_SCALAR_SCALE 0
 #endif
-template <int EVERY>
+#ifndef IEF_TC3_EMUL_IN_TURN
+#define IEF_TC3_EMUL_IN_TURN 1   // 1: the emulated pairs are interleaved with the MUFU ones inside the exp section; 0: before the turn
+#endif
+template <int EVERY_>
 __device__ __forceinline__ void scale_chunk_mix(uint32_t (&s)[32], float2 c2, float2 nmc) {
+  constexpr int EVERY = IEF_TC3_EMUL_IN_TURN ? 0 : EVERY_;
 #pragma unroll
   for (int i = 0; i < 32; i += 2) {
 #if IEF_SCALAR_SCALE
@@ -126,6 +132,13 @@ __device__ __forceinline__ void scale_chunk_mix(uint32_t (&s)[32], float2 c2, fl
     s[i + 1] = __float_as_uint(x.y);
   }
 }
+
+// PERFORMANCE DIAGNOSTIC ONLY (wrong results): -DIEF_TC3_DIAG_SKIP_EXP=n drops the exponential of every n-th column pair (n = 1: all of
+// them) to measure how much of the kernel's time the MUFU pipe really accounts for.
+#ifndef IEF_TC3_DIAG_SKIP_EXP
+#define IEF_TC3_DIAG_SKIP_EXP 0
+#endif
+__device__ __forceinline__ constexpr bool diag_skip_exp(int pair) { return IEF_TC3_DIAG_SKIP_EXP > 0 && pair % (IEF_TC3_DIAG_SKIP_EXP > 0 ? IEF_TC3_DIAG_SKIP_EXP : 1) == 0; }
 
 // Row sums in registers (head_dim > 48: no accumulator columns left for the row-sum MMA). bf16: the sum is taken over the SAME 16-bit
 // values the PV MMA multiplies — the fp32 exponentials cut to their upper halves (2 LOP3 + 1 PRMT instead of 1 F2FP per pair) — so that
@@ -141,7 +154,9 @@ __device__ __forceinline__ void exp_pack_chunk_mix(const uint32_t (&s)[32], uint
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     float2 x = make_float2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1]));
-    if (!emul_pair<EVERY>(i)) { x.x = ief_exp2(x.x); x.y = ief_exp2(x.y); }
+    if (diag_skip_exp(i)) { x.x = fmaf(x.x, 1e-3f, 0.5f); x.y = fmaf(x.y, 1e-3f, 0.5f); }
+    else if (!emul_pair<EVERY>(i)) { x.x = ief_exp2(x.x); x.y = ief_exp2(x.y); }
+    else if (IEF_TC3_EMUL_IN_TURN) x = exp2_fma(x);
     if constexpr (cut) {
       const uint32_t lo = __float_as_uint(x.x) & 0xffff0000u, hi = __float_as_uint(x.y) & 0xffff0000u;
       x = make_float2(__uint_as_float(lo), __uint_as_float(hi));
@@ -159,7 +174,9 @@ __device__ __forceinline__ void exp_pack_chunk_nosum(const uint32_t (&s)[32], ui
 #pragma unroll
   for (int i = BEGIN; i < END; ++i) {
     float2 x = make_float2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1]));
-    if (!emul_pair<EVERY>(i)) { x.x = ief_exp2(x.x); x.y = ief_exp2(x.y); }
+    if (diag_skip_exp(i)) { x.x = fmaf(x.x, 1e-3f, 0.5f); x.y = fmaf(x.y, 1e-3f, 0.5f); }
+    else if (!emul_pair<EVERY>(i)) { x.x = ief_exp2(x.x); x.y = ief_exp2(x.y); }
+    else if (IEF_TC3_EMUL_IN_TURN) x = exp2_fma(x);
     u[i] = E::pack(x.x, x.y);
   }
 }

@@ -648,3 +648,21 @@ def test_fused_ddim_refuses_scheduler_configs_it_does_not_implement(field, value
     setattr(sched.config, field, value)
     with pytest.raises(ValueError, match=field):
         FusedDDIM(sched)
+
+
+@pytest.mark.parametrize("cfg_name,kind", [("sd15_slim", "masactrl_union"), ("sd15_slim", "p2p_refine")])
+def test_full_geometry_host_logic_reproduces_reference(monkeypatch, cfg_name, kind):
+    """The 64x64-latent, real-head-dim scenarios (tests/golden/fullgeo_*.pt) through this package's closures + controllers with the
+    oracle-backed fp32 ops: the row tables / second key block (Union) and the edit tables (refine) at the BASELINE geometry, 2e-4."""
+    import image_editing_framework_b200 as pkg
+    from image_editing_framework_b200 import masactrl, pnp  # noqa: F401
+    cpu_backend.install(monkeypatch)
+    g = golden(f"fullgeo_{cfg_name}_{kind}.pt")
+    api = {"p2p": pkg.p2p, "masactrl": pkg.masactrl, "pnp": pkg.pnp}[kind.split("_")[0]]
+    ctrl, records, per_step = scenarios.run_fullgeo(cfg_name, kind, api, torch.device("cpu"))
+    for step, outs in g["layer_outputs"].items():
+        for i, (a, b) in enumerate(zip(records[step], outs)):
+            assert (a - b).abs().max().item() < 2e-4, f"layer {i}"
+    for a, b in zip(per_step, g["latents_per_step"]):
+        assert (a - b).abs().max().item() < 1e-3
+    assert ctrl.cur_step == g["cur_step"]
