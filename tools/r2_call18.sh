@@ -1,0 +1,7 @@
+#!/usr/bin/env bash
+mkdir -p gpurun_out
+V=image_editing_framework_b200/csrc/build/variants
+for v in freerun scaleturn late freescale; do
+  IEF_LIB_PATH=$V/libief_b200_$v.so timeout 300 python tools/bench_attn.py tcgen05 big nosdpa > gpurun_out/r2c18_bench_$v.jsonl 2>&1; echo "$v exit $?"
+done
+for v in freerun scaleturn late freescale; do echo "--- $v"; grep -h tcgen05 gpurun_out/r2c18_bench_$v.jsonl | cut -c1-60,128-190; done
