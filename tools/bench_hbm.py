@@ -94,7 +94,7 @@ def main():
     wa[:, 3] = 1
     xt = torch.randn(2, 4, 64, 64, device=dev)
     ms = time_call(lambda: ops.local_blend(xt, maps, 2, wa, 0.3))
-    report("local_blend (5 maps of 16x16, 2 launches + memset)", ms, sum(m.numel() for m in maps) * 4 // 77 * 32 + 2 * xt.numel() * 4, "only the selected words' sectors are read")
+    report("local_blend (5 maps of 16x16, 2 launches)", ms, sum(m.numel() for m in maps) * 4 // 77 * 32 + 2 * xt.numel() * 4, "only the selected words' sectors are read")
 
 
 if __name__ == "__main__":
