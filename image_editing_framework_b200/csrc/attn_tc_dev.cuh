@@ -25,7 +25,8 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
   return d;
 }
 
-// one 32-column chunk of scores -> probabilities (packed 16-bit pairs), accumulating the fp32 row sum
+// one 32-column chunk of scores -> probabilities (packed 16-bit pairs), accumulating the fp32 row sum. bf16: the sum is taken over the
+// same 16-bit values the PV MMA multiplies (see exp_pack_chunk_mix below for why)
 template <typename E>
 __device__ __forceinline__ void exp_chunk(const uint32_t (&s)[32], uint32_t (&u)[16], float2 c2, float2 nmc, float2& acc0, float2& acc1) {
 #pragma unroll
@@ -34,10 +35,19 @@ __device__ __forceinline__ void exp_chunk(const uint32_t (&s)[32], uint32_t (&u)
     float2 x1 = ffma2(make_float2(__uint_as_float(s[2 * i + 2]), __uint_as_float(s[2 * i + 3])), c2, nmc);
     x0.x = ief_exp2(x0.x); x0.y = ief_exp2(x0.y);
     x1.x = ief_exp2(x1.x); x1.y = ief_exp2(x1.y);
+    if constexpr (E::kIsBf16) {
+      const uint32_t a0 = __float_as_uint(x0.x) & 0xffff0000u, b0 = __float_as_uint(x0.y) & 0xffff0000u;
+      const uint32_t a1 = __float_as_uint(x1.x) & 0xffff0000u, b1 = __float_as_uint(x1.y) & 0xffff0000u;
+      x0 = make_float2(__uint_as_float(a0), __uint_as_float(b0));
+      x1 = make_float2(__uint_as_float(a1), __uint_as_float(b1));
+      u[i] = __byte_perm(a0, b0, 0x7632);
+      u[i + 1] = __byte_perm(a1, b1, 0x7632);
+    } else {
+      u[i] = E::pack(x0.x, x0.y);
+      u[i + 1] = E::pack(x1.x, x1.y);
+    }
     acc0 = fadd2(acc0, x0);
     acc1 = fadd2(acc1, x1);
-    u[i] = E::pack(x0.x, x0.y);
-    u[i + 1] = E::pack(x1.x, x1.y);
   }
 }
 

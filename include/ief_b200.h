@@ -123,6 +123,9 @@ int ief_attn_fwd(const ief_attn_params* p, void* stream);
  * probs_out (optional fp32 [B,H,Nq,Nk]) receives P_b' (post-edit, what a reader of
  * AttentionStore sees, attention_base.py:67 stores by alias) of every row with store_slot[b] >= 0
  * (probs_out is [n_stored, H, Nq, Nk]), overwriting or accumulating (probs_accum).
+ * Kernels: with >= 128 queries the plain, unstored rows run on cross_tc.cu and the edited / stored rows on
+ * cross_tc_edit.cu (both tcgen05 / TMEM / TMA; the edit needs the sparse form of a REPLACE mapper); fewer queries
+ * or a dense-only mapper take the mma.sync kernel (cross_attn.cu). Same results within rounding either way.
  */
 typedef enum ief_edit_mode { IEF_EDIT_NONE = 0, IEF_EDIT_REPLACE = 1, IEF_EDIT_REFINE = 2 } ief_edit_mode;
 
@@ -250,7 +253,8 @@ const char* ief_last_error(void);
 int64_t ief_launch_count(void);
 /* name of the kernel family the last ief_attn_fwd call dispatched to ("tcgen05" / "mma") */
 const char* ief_last_attn_impl(void);
-/* the same for the last ief_cross_attn_edit_fwd call of this thread ("tcgen05" = cross_tc.cu, "mma" = cross_attn.cu) */
+/* the same for the last ief_cross_attn_edit_fwd call of this thread: "tcgen05" (cross_tc.cu only), "tcgen05-edit"
+ * (cross_tc_edit.cu, plus cross_tc.cu for the call's plain rows), "mma" (cross_attn.cu) */
 const char* ief_last_cross_impl(void);
 /* 0 when a CUDA device with compute capability 10.x is current */
 int ief_check_device(void);

@@ -534,6 +534,10 @@ def test_edits_at_baseline_attention_geometry_match_reference(cuda, cfg_name, ki
     # probability sweep behind it where maps are stored), and for the plain cross-attention rows of the large layers
     big_self = [c for c in log.calls if c[0] == "self" and c[1] >= 1024]
     assert big_self and all(c[3] in ("tcgen05", "tcgen05+probs") for c in big_self), sorted(set(big_self))
+    if kind.startswith("p2p"):   # edited / stored cross-attention rows of the large layers: the tensor-pipe edit kernel
+        big_cross = [c for c in log.calls if c[0] == "cross" and c[1] >= 1024]
+        want = {"p2p_replace": "tcgen05-edit", "p2p_refine": "tcgen05-edit", "p2p_store": "tcgen05-edit"}[kind]
+        assert big_cross and any(c[3] == want for c in big_cross) and all(c[3] in ("tcgen05", "tcgen05-edit") for c in big_cross), sorted(set(big_cross))
     if kind == "masactrl":       # (PnP hooks eight self-attention layers only: its cross-attention stays the UNet's own)
         big_cross = [c for c in log.calls if c[0] == "cross" and c[1] >= 1024]
         assert big_cross and all(c[3] == "tcgen05" for c in big_cross), sorted(set(big_cross))

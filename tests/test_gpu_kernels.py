@@ -361,8 +361,18 @@ def test_cross_attention_edit(cuda, mode, equalize, shape):
     got = ops.cross_attention_edit(q.to(cuda), k.to(cuda), v.to(cuda), H, scale, edit=edit, step_alpha=alpha.to(cuda).contiguous(),
                                    base_row=base, edit_slot=slot, probs_out=store, store_slot=sslot)
     torch.cuda.synchronize()
+    # which kernel served it: the tensor-pipe edit kernel from 128 queries on, unless the mapper only exists in its dense form
+    assert _cabi.last_cross_impl() == ("tcgen05-edit" if N >= 128 and mode != "replace_dense" else "mma")
     assert (got.float().cpu() - want_o).abs().max().item() < TOL * (4 if equalize else 1)
     assert (store.cpu() - edited[lo * H:]).abs().max().item() < 5e-3 * (4 if equalize else 1)
+    # the same call without the map output and accumulating into a pre-filled store (other template flavours of the kernel)
+    got2 = ops.cross_attention_edit(q.to(cuda), k.to(cuda), v.to(cuda), H, scale, edit=edit, step_alpha=alpha.to(cuda).contiguous(),
+                                    base_row=base, edit_slot=slot)
+    assert (got2.float() - got.float()).abs().max().item() < 1e-2
+    ops.cross_attention_edit(q.to(cuda), k.to(cuda), v.to(cuda), H, scale, edit=edit, step_alpha=alpha.to(cuda).contiguous(),
+                             base_row=base, edit_slot=slot, probs_out=store, probs_accum=True, store_slot=sslot)
+    torch.cuda.synchronize()
+    assert (store.cpu() - 2 * edited[lo * H:]).abs().max().item() < 1e-2 * (4 if equalize else 1)
 
 
 def test_cross_attention_plain_matches_self_kernel(cuda):
