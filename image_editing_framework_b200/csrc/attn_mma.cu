@@ -169,17 +169,40 @@ attn_mma_kernel(const __grid_constant__ MmaArgs a) {
         // normalised probabilities -> global fp32 (each quad writes one full 32-byte sector per row)
         const int64_t prow = ((int64_t)a.rows.pslot[b] * a.H + h) * a.Nq;
         const int col0 = (blk2 ? a.Nk : 0) + jj * kBN;
+        if (vc == kBN && ((nk_total | col0) & 1) == 0) {
+          // full tile, 8-byte aligned pairs; accumulating: the old pairs of four column blocks are requested together before the first
+          // of their stores (load / add / store per element strings one DRAM round trip per element together, see
+          // attn_probs_from_lse_kernel)
+          float2* d0 = reinterpret_cast<float2*>(a.probs + (prow + grow0) * nk_total + col0 + 2 * t);
+          float2* d1 = reinterpret_cast<float2*>(a.probs + (prow + grow0 + 8) * nk_total + col0 + 2 * t);
+          const bool r0 = grow0 < a.Nq, r1 = grow0 + 8 < a.Nq;
 #pragma unroll
-        for (int nb = 0; nb < 8; ++nb) {
-          const int c = nb * 8 + 2 * t;
+          for (int g4 = 0; g4 < 8; g4 += 4) {
+            float2 o0[4], o1[4];
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            const int r = grow0 + hh * 8;
-            if (r < a.Nq) {
-              float* dst = a.probs + (prow + r) * nk_total + col0 + c;
-              const float p0 = s[nb][2 * hh], p1 = s[nb][2 * hh + 1];
-              if (c < vc) dst[0] = a.probs_accum ? dst[0] + p0 : p0;
-              if (c + 1 < vc) dst[1] = a.probs_accum ? dst[1] + p1 : p1;
+            for (int i = 0; i < 4; ++i) {
+              o0[i] = (a.probs_accum && r0) ? d0[(g4 + i) * 4] : make_float2(0.f, 0.f);
+              o1[i] = (a.probs_accum && r1) ? d1[(g4 + i) * 4] : make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              if (r0) d0[(g4 + i) * 4] = make_float2(o0[i].x + s[g4 + i][0], o0[i].y + s[g4 + i][1]);
+              if (r1) d1[(g4 + i) * 4] = make_float2(o1[i].x + s[g4 + i][2], o1[i].y + s[g4 + i][3]);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int nb = 0; nb < 8; ++nb) {
+            const int c = nb * 8 + 2 * t;
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              const int r = grow0 + hh * 8;
+              if (r < a.Nq) {
+                float* dst = a.probs + (prow + r) * nk_total + col0 + c;
+                const float p0 = s[nb][2 * hh], p1 = s[nb][2 * hh + 1];
+                if (c < vc) dst[0] = a.probs_accum ? dst[0] + p0 : p0;
+                if (c + 1 < vc) dst[1] = a.probs_accum ? dst[1] + p1 : p1;
+              }
             }
           }
         }

@@ -359,6 +359,15 @@ extern "C" int ief_cross_attn_edit_fwd(const ief_cross_params* p, void* stream) 
     }
     if (edit_on) {
       g_last_cross_impl = "tcgen05-edit";
+      // The call's plain rows ride in the edit kernel's launch, after the edited ones (longest CTAs first): a second, serialised launch
+      // of the leaner plain kernel costs more than it saves (N=4096,d=40: 31.7 -> 28.7 us; N=1024,d=80: 23.6 -> 18.5; N=256,d=160:
+      // 23.5 -> 14.4). IEF_CROSS_TC_ONE_LAUNCH=0 restores the two launches (A/B).
+      static int one = -1;
+      if (one < 0) { const char* e = getenv("IEF_CROSS_TC_ONE_LAUNCH"); one = (e && e[0] == '0') ? 0 : 1; }
+      if (one) {
+        for (int i = 0; i < np; ++i) special[ns + i] = plain[i];
+        return ief_cross_tc_edit_launch(p, special, ns + np, st);
+      }
       int rc = ief_cross_tc_edit_launch(p, special, ns, st);
       if (rc != IEF_OK || np == 0) return rc;
       return ief_cross_tc_launch(p, st, plain, np);
