@@ -208,9 +208,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             if (32 * c + 2 * i >= vc) p0 = 0.f;
             if (32 * c + 2 * i + 1 >= vc) p1 = 0.f;
           }
+          if constexpr (E::kIsBf16) {  // the row sum over the same 16-bit values the PV MMA multiplies (attn_tc_dev.cuh, exp_pack_chunk_mix)
+            const uint32_t b0 = __float_as_uint(p0) & 0xffff0000u, b1 = __float_as_uint(p1) & 0xffff0000u;
+            p0 = __uint_as_float(b0);
+            p1 = __uint_as_float(b1);
+            u[i] = __byte_perm(b0, b1, 0x7632);
+          } else {
+            u[i] = E::pack(p0, p1);
+          }
           lsum0 += p0;
           lsum1 += p1;
-          u[i] = E::pack(p0, p1);
         }
         tmem_st16(tP + 16 * c, u);
       }

@@ -362,7 +362,8 @@ def test_cross_attention_edit(cuda, mode, equalize, shape):
                                    base_row=base, edit_slot=slot, probs_out=store, store_slot=sslot)
     torch.cuda.synchronize()
     # which kernel served it: the tensor-pipe edit kernel from 128 queries on, unless the mapper only exists in its dense form
-    assert _cabi.last_cross_impl() == ("tcgen05-edit" if N >= 128 and mode != "replace_dense" else "mma")
+    on_tensor_pipe = N >= 128 and mode != "replace_dense" and os.environ.get("IEF_CROSS_TC", "1") != "0" and os.environ.get("IEF_CROSS_TC_EDIT", "1") != "0"
+    assert _cabi.last_cross_impl() == ("tcgen05-edit" if on_tensor_pipe else "mma")
     assert (got.float().cpu() - want_o).abs().max().item() < TOL * (4 if equalize else 1)
     assert (store.cpu() - edited[lo * H:]).abs().max().item() < 5e-3 * (4 if equalize else 1)
     # the same call without the map output and accumulating into a pre-filled store (other template flavours of the kernel)
