@@ -13,7 +13,7 @@
 // Why 20 warps: the exp pipe (MUFU, 8 cycles per warp instruction per SM sub-partition) is the binding unit at head_dim
 // 40-64 and one softmax warp per sub-partition only keeps it 84 % busy (two: 98 %, tools/micro/mufu.cu). Each stream's
 // softmax is therefore spread over TWO warpgroups owning the left / right 64 score columns of every row:
-//   warp 0   TMA producer      warp 1   tcgen05.mma issuer (elected lane)      warps 2,3   idle register donors (setmaxnreg)
+//   warp 0   TMA producer      warps 1, 2   tcgen05.mma issuers, one per stream (elected lane)      warp 3   idle register donor (setmaxnreg)
 //   warps 4-11   stream 0: columns 0-63 (warps 4-7) and 64-127 (warps 8-11)      warps 12-19   stream 1 likewise
 // The halves of a row exchange their partial row maximum through shared memory (one 256-thread named barrier per key
 // tile); partial row sums are merged in the epilogue; each half rescales / writes back its share of the O columns.
@@ -21,8 +21,11 @@
 // lock-step and idle the MUFU together. Scale/shift (FMA pipe) happens before a stream takes its turn, and the turn is
 // handed over one 32-column chunk early so the other stream's wake-up overlaps the tail.
 //
-// Measured (tools/tc3_trace.py): what bounds the kernel is the instruction stream of the four softmax warps per sub-partition,
-// not the MUFU alone, so two compile-time variants delete instructions from it:
+// What bounded generations 3-3c (round 2, profiles/r02_tc3_no_exp_diagnostic.txt): with every exponential removed the kernel was NOT
+// faster. A tcgen05.mma group needs ~300 clk from issue to its barrier, and ONE issuer warp walking QK_0 QK_1 PV_0 PV_1 with a blocking
+// wait before each strung four such round trips (each answered by the softmax side) together per key tile: ~2350 clk, the same as two
+// ordered exp sections. Hence one issuer warp per stream (kDualIssue) — after which the exp pipe binds and a quarter of the
+// exponentials go to the FMA pipe (IEF_TC3_EMUL). The compile-time variants below delete softmax-warp instructions:
 //   SUMMMA  head_dim <= 48: row sums come from an extra [128 x 16] = P x ones MMA into the accumulator columns left free after O
 //           (same fp32 accumulation and lazy rescale as O) instead of 32 packed adds per row and tile
 //   MAXMODE 1 (SKIP)   bf16 with a key-norm pre-pass (TcArgs::knorm): tiles whose Cauchy-Schwarz score bound is provably harmless
