@@ -460,13 +460,14 @@ int ief_attn_tc_launch(const ief_attn_params* p, const IefRowTable& rows, cudaSt
       force = e ? atoi(e) : -1;
     }
     const int sms = ief_sm_count();
-    // estimated time in units of one key step: waves x (steps per CTA + ~3 steps of prologue/epilogue)
+    // estimated time in units of one key step (~2.25 K cycles): waves x (steps per CTA + fixed cost). Measured fixed costs (tools/tc3_trace.py):
+    // ~8.5 K cycles = 4 steps per pair CTA, one more for a split-KV CTA's merge, and ~3 steps for the gap before a second launch
     const int nt = a.nt1 + a.nt2;
     const long pairs = (long)ief_ceil_div(p->Nq, 2 * kBM) * p->H * p->B;
     const long full = pairs / sms, rest = pairs % sms;
-    const long t_pair = (full + (rest ? 1 : 0)) * (nt + 3);
-    const long t_split = ((2 * pairs + sms - 1) / sms) * ((nt + 1) / 2 + 3);
-    const long t_hybrid = full * (nt + 3) + ((2 * rest + sms - 1) / sms) * ((nt + 1) / 2 + 3) + (rest ? 1 : 0);  // +1: second launch
+    const long t_pair = (full + (rest ? 1 : 0)) * (nt + 4);
+    const long t_split = ((2 * pairs + sms - 1) / sms) * ((nt + 1) / 2 + 5);
+    const long t_hybrid = full * (nt + 4) + ((2 * rest + sms - 1) / sms) * ((nt + 1) / 2 + 5) + (rest ? 3 : 0);
     int mode = 0;  // 0 pair, 1 split, 2 hybrid
     if (force >= 0) mode = force;
     else if (t_hybrid < t_pair && t_hybrid <= t_split && full > 0 && rest > 0) mode = 2;

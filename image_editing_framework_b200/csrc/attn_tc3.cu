@@ -54,7 +54,10 @@ namespace {
 constexpr int kBM = 128, kBN = 128;
 constexpr int kThreads = 640;
 constexpr int kRegsLow = 32, kRegsHigh = 112;  // pool = 640 threads x 96 regs at launch (61440): 128*32 + 512*112 = 61440
-constexpr int ST = 3;
+#ifndef IEF_TC3_STAGES
+#define IEF_TC3_STAGES 3
+#endif
+constexpr int ST = IEF_TC3_STAGES;   // K / V ring depth (4: no gain, profiles/r02 notes)
 constexpr int kTile = kTcChunkBytes;           // 16 KiB: one [128 x 64ch] box (head_dim <= 64)
 constexpr int kSmemOnes = 2 * 1024;            // [16 x 64] tile of 1.0 (K-major, SWIZZLE_128B footprint): B operand of the row-sum MMA
 constexpr int kSmemXchg = 8 * 1024;            // floats: row-max exchange [2 parities][2 streams][2 halves][128] | row sums [2][2][128] | split merge [2][128]
