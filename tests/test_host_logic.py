@@ -666,3 +666,26 @@ def test_full_geometry_host_logic_reproduces_reference(monkeypatch, cfg_name, ki
     for a, b in zip(per_step, g["latents_per_step"]):
         assert (a - b).abs().max().item() < 1e-3
     assert ctrl.cur_step == g["cur_step"]
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`python bench.py --impl reference` (debug-sized) prints exactly ONE JSON line on stdout with the contract's keys, the same `config`
+    object our arm prints, and a step time that is a real wall time (not the extrapolated edit)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--config", "tiny", "--ddim-steps", "4", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=600, check=True).stdout
+    lines = [l for l in out.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    line = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+                "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["unit"] == "edits/s" and line["vs_baseline"] is None and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["extrapolated"] is True
+    assert line["e2e"] == {"value": line["value"], "unit": "edits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    import bench
+    assert line["config"] == bench.workload_config(4, "tiny")
+    assert line["ms_per_step"] < 1e3 * 60 and line["ms_per_edit_extrapolated"] > 0
