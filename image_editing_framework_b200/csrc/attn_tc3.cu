@@ -68,6 +68,9 @@ constexpr int kSmemXchg = 8 * 1024;            // floats: row-max exchange [2 pa
 #define IEF_TC3_TRACE 0
 #endif
 #define IEF_TC3_FINE_TRACE (IEF_TC3_TRACE >= 2)
+#ifndef IEF_TC3_TRACE_ITEM
+#define IEF_TC3_TRACE_ITEM 0  // which of a persistent CTA's items gets the per-tile stamps
+#endif
 #ifndef IEF_TC3_HANDOVER_LATE
 #define IEF_TC3_HANDOVER_LATE 0  // experiment: hand the turn over after the whole exp section instead of one chunk early
 #endif
@@ -101,6 +104,22 @@ constexpr bool kFastOrdered = IEF_TC3_FAST_ORDERED != 0;
 #define IEF_TC3_DUAL_ISSUE 1
 #endif
 constexpr bool kDualIssue = IEF_TC3_DUAL_ISSUE != 0;
+// Persistent 256-row CTAs: one CTA per SM walks its share of the work items (item = first + blockIdx.x + i * gridDim.x) with TMEM,
+// barriers and tensor maps set up once. Nothing is drained between items: the producer fetches the next Q as soon as the last QK^T of
+// the current item has completed and runs ahead in the K / V ring, each issuer puts S(0) of the next item into TMEM as soon as the
+// last score tile of the current one sits in the softmax registers, so that a stream's epilogue (~2.5 K cycles) overlaps the other
+// stream's exp sections and the next item's first exp section starts right behind it. All barriers simply keep counting: the phase
+// parities of item number k are those of item 0 xor (k odd ? phases per item, per barrier : 0) (PbSeq), the same mechanism as the
+// exact second pass. An item whose unshifted row sums leave the safe range (MAXMODE 2) is only flagged; flagged items are repeated
+// with the exact loop after the CTA's last item (one rendezvous per CTA instead of one per item).
+#ifndef IEF_TC3_PERSIST
+#define IEF_TC3_PERSIST 1
+#endif
+constexpr bool kPersist = IEF_TC3_PERSIST != 0;
+#ifndef IEF_TC3_PIN_BAR0
+#define IEF_TC3_PIN_BAR0 1
+#endif
+constexpr int kMaxItemsPerCta = 32;  // bits of the redo mask
 
 // mbarrier phase-parity bases of a pass: zero for the first (or only) pass; for the exact second pass of a MAXMODE 2 CTA the number
 // of phases each barrier completed during the first pass, mod 2
@@ -108,12 +127,22 @@ struct PbZero {
   __device__ __forceinline__ int stage(int) const { return 0; }
   __device__ __forceinline__ int strm(int) const { return 0; }
   __device__ __forceinline__ int turn(int) const { return 0; }
+  __device__ __forceinline__ int item() const { return 0; }
 };
 struct PbPass2 {
-  uint32_t m;  // bits 0..2: ring stages, 4..5: per-stream barriers (S, P, C, O), 6..7: exp-turn barriers
+  uint32_t m;  // bits 0..3: ring stages, 4..5: per-stream barriers (S, P, C, O), 6..7: exp-turn barriers
   __device__ __forceinline__ int stage(int s) const { return (m >> s) & 1; }
   __device__ __forceinline__ int strm(int t) const { return (m >> (4 + t)) & 1; }
   __device__ __forceinline__ int turn(int t) const { return (m >> (6 + t)) & 1; }
+  __device__ __forceinline__ int item() const { return 0; }  // the second pass re-uses the Q tile: no new phase of the Q barrier
+};
+struct PbSeq {  // persistent CTAs: bases of the k-th item of a CTA (k items done, each advanced every barrier by the same number of phases)
+  uint32_t stages;  // bit s: ring stage s
+  int kk;           // Q loaded / Q free / O drained: one phase per item
+  __device__ __forceinline__ int stage(int s) const { return (stages >> s) & 1; }
+  __device__ __forceinline__ int strm(int) const { return 0; }  // per-stream (S, P, C, O) and exp-turn barriers: nt phases per item, nt even
+  __device__ __forceinline__ int turn(int) const { return 0; }
+  __device__ __forceinline__ int item() const { return kk; }
 };
 template <bool V> struct BoolTag { static constexpr bool value = V; };
 
@@ -129,7 +158,7 @@ __device__ __forceinline__ float approx_sqrt(float x) { float y; asm("sqrt.appro
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
-template <int DTYPE, bool SPLIT, int EMUL, bool SUMMMA, int MAXMODE, bool BIAS>
+template <int DTYPE, bool SPLIT, int EMUL, bool SUMMMA, int MAXMODE, bool BIAS, bool PERSIST>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                 const __grid_constant__ TcArgs a) {
@@ -138,12 +167,26 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   constexpr int RT = Cfg::kRingTiles;
   constexpr bool SKIP = MAXMODE == 1, NOMAX = MAXMODE == 2;
   static_assert(!(NOMAX && BIAS), "the unshifted loop has no key-bias form");
-  // 1-D grid over linearised work items so that a launch can cover any contiguous range of them (hybrid pair + split launches)
-  const int lin = blockIdx.x + a.work_offset;
-  const int qt = lin % a.nq_blocks;  // 256-row block (pair) or 128-row tile (split)
-  const int h = (lin / a.nq_blocks) % a.H, b = lin / (a.nq_blocks * a.H);
-  if (!a.rows.active[b]) return;
-  const bool cta_trace = a.dbg != nullptr && lin == 0;
+  // persistent form: 256-row flavour only (the split flavour stages its merge in the K ring), not for the key-norm variant (its
+  // softmax warps read the Q tile), the unshifted loop must take exp turns like the exact one (same phases per item), and the launcher
+  // only picks it for an EVEN number of key tiles per item: the per-tile barriers then advance an even number of phases per item and
+  // the softmax warps, whose instruction issue bounds the kernel, need no parity bases at all
+  static_assert(!PERSIST || (!SPLIT && !SKIP && kFastOrdered), "persistent form: 256-row flavour, not the key-norm variant, ordered exp sections");
+  // 1-D grid over linearised work items so that a launch can cover any contiguous range of them (hybrid pair + split launches);
+  // a persistent CTA takes the items blockIdx.x, blockIdx.x + gridDim.x, ... of the launch's n_items
+  int qt, h, b;  // 256-row block (pair) or 128-row tile (split), head, batch row of the current item: every thread walks the same sequence
+  auto set_item = [&](int it) -> bool {
+    const int lin = a.work_offset + (int)blockIdx.x + it * (int)gridDim.x;
+    qt = lin % a.nq_blocks;
+    h = (lin / a.nq_blocks) % a.H;
+    b = lin / (a.nq_blocks * a.H);
+    return a.rows.active[b] != 0;
+  };
+  const int n_local = PERSIST ? (a.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 1;
+  if constexpr (!PERSIST) {
+    if (!set_item(0)) return;
+  }
+  const bool cta_trace = a.dbg != nullptr && blockIdx.x + a.work_offset == 0;
   if (cta_trace && threadIdx.x == 0) a.dbg[1536] = clock64();
 
   extern __shared__ uint8_t smem_raw[];
@@ -158,7 +201,11 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   float* xsum = xmax + 2 * 2 * 2 * 128;                                       // [stream][half][128]
   float* xml = xsum + 2 * 2 * 128;                                            // split merge: [0..127] max, [128..255] sum of stream 1
   float* xq = xml + 256;                                   // [2 streams][8 warps][2]: one-time (max |q|, min row max) exchange
-  const uint32_t bar0 = base + Cfg::kSmemData + kSmemOnes + kSmemXchg;
+  uint32_t bar0_ = base + Cfg::kSmemData + kSmemOnes + kSmemXchg;
+#if IEF_TC3_PIN_BAR0
+  if constexpr (PERSIST) asm volatile("" : "+r"(bar0_));  // one register instead of re-deriving the shared-memory window address inside the key loop
+#endif
+  const uint32_t bar0 = bar0_;
   const uint32_t bar_q = bar0;
   auto bar_s = [&](int t) { return bar0 + 8 + 8 * t; };    // S_t complete in TMEM
   auto bar_p = [&](int t) { return bar0 + 24 + 8 * t; };   // P_t written by the 256 softmax threads of stream t
@@ -169,9 +216,11 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   auto bar_ke = [&](int s) { return bar0 + 88 + 8 * (ST + s); };
   auto bar_vf = [&](int s) { return bar0 + 88 + 8 * (2 * ST + s); };
   auto bar_ve = [&](int s) { return bar0 + 88 + 8 * (3 * ST + s); };
-  const uint32_t tmem_slot = bar0 + 88 + 32 * ST;
+  const uint32_t bar_qe = bar0 + 88 + 32 * ST;                            // persistent: every QK^T of the current item has completed (Q tile free)
+  auto bar_d = [&](int t) { return bar0 + 88 + 32 * ST + 8 + 8 * t; };   // persistent: the epilogue of stream t has read O_t out of TMEM
+  const uint32_t tmem_slot = bar0 + 88 + 32 * ST + 24;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
-  volatile uint32_t* redo_flag = tmem_slot_ptr + 2;  // MAXMODE 2: some row sum of the unshifted pass left the safe range
+  volatile uint32_t* redo_flag = tmem_slot_ptr + 2;  // MAXMODE 2: some row sum of the unshifted pass left the safe range (persistent: bit i = i-th item)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nt = a.nt1 + a.nt2;
@@ -198,6 +247,24 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     if (kFastOrdered) pb.m |= (uint32_t)(nt1 & 1) << 6 | (uint32_t)(nt0 & 1) << 7;  // bar_x(t) completes once per section of stream t^1
     return pb;
   };
+  auto seq_bases = [&](int k) {  // persistent (256-row flavour: nt0 == nt1 == nt, even)
+    PbSeq pb;
+    pb.stages = (k & 1) ? (pass2_bases().m & 0xfu) : 0u;
+    pb.kk = k & 1;
+    return pb;
+  };
+  // The items of a persistent CTA: entry e < n_local is item e in its first (or only) form; with the unshifted loop, entries n_local
+  // ... 2 n_local - 1 are the exact repeats of the flagged items, after one CTA-wide rendezvous. Returns the item index or -1 (skip),
+  // -2 (done). Every thread of the CTA walks the same sequence; the state carried across an item is just (e, k).
+  auto next_entry = [&](int e, bool& exact) -> int {
+    exact = !NOMAX;
+    if (e < n_local) return e;
+    if (e == n_local) named_bar_sync(0, kThreads);  // the softmax warps have looked at the row sums of every item
+    const uint32_t redo = *redo_flag;
+    if (redo == 0) return -2;
+    exact = true;
+    return ((redo >> (e - n_local)) & 1) ? e - n_local : -1;
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -210,7 +277,9 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(bar_c(t), 8);
       mbar_init(bar_o(t), 1);
       mbar_init(bar_x(t), 8);
+      mbar_init(bar_d(t), 8);
     }
+    mbar_init(bar_qe, kDualIssue ? 2 : 1);
     for (int s = 0; s < ST; ++s) {
       mbar_init(bar_kf(s), 1);
       mbar_init(bar_ke(s), kDualIssue ? 2 : 1);
@@ -240,9 +309,12 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (cta_trace && threadIdx.x == 0) a.dbg[1537] = clock64();
 
   // ------------------------------------------------------------------ TMA producer (warp 0)
-  auto producer = [&](auto pb, bool load_q) {
+  auto producer = [&](auto pb, bool load_q, int k) {
     const int qb = a.rows.q[b];
     if (load_q) {
+      if constexpr (PERSIST) {
+        if (k > 0) mbar_wait(bar_qe, (k - 1) & 1);  // the previous item's last QK^T has read the Q tile
+      }
       if (elect_one()) {
         mbar_arrive_expect_tx(bar_q, Cfg::kQTiles * kTile);
         for (int t = 0; t < Cfg::kQTiles; ++t) tc_tma_tile(sQ(t), &tmQ, bar_q, 0, (Cfg::kQTiles * qt + t) * kBM, h, qb, a.perm_q);
@@ -276,7 +348,7 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   };
 
   // ------------------------------------------------------------------ MMA issuer (warp 1: whole warp waits, one elected lane issues)
-  auto mma_issuer = [&](auto pb, int t_lo, int t_hi) {
+  auto mma_issuer = [&](auto pb, int t_lo, int t_hi, int k) {
     const uint64_t desc_k = make_smem_desc_sw128(0, 16, 1024);
     const uint64_t desc_v = make_smem_desc_sw128(0, kTcChunkBytes, 1024);
     auto issue_qk = [&](int t, int s) {
@@ -300,14 +372,21 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     auto release = [&](uint32_t bar, bool issued) {
       if (issued) umma_commit(bar); else mbar_arrive(bar);
     };
-    mbar_wait(bar_q, 0);
+    mbar_wait(bar_q, pb.item());
     mbar_wait(bar_kf(0), pb.stage(0));
+    if constexpr (PERSIST) {
+      if (k > 0)  // S_t still holds the previous item's last score tile until its softmax warps have it in registers
+        for (int t = t_lo; t < t_hi; ++t) mbar_wait(bar_c(t), pb.strm(t) ^ 1);
+    }
     tc_fence_after();
     if (elect_one()) {
       bool any = false;
       for (int t = t_lo; t < t_hi; ++t)
         if (stream_nt(t) > 0) { issue_qk(t, 0); any = true; }
       release(bar_ke(0), any);
+      if constexpr (PERSIST) {
+        if (nt0 == 1) umma_commit(bar_qe);
+      }
     }
     __syncwarp();
     for (int j = 0; j < nt0; ++j) {
@@ -325,7 +404,12 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             any = true;
           }
         }
-        if (elect_one()) release(bar_ke(s1), any);
+        if (elect_one()) {
+          release(bar_ke(s1), any);
+          if constexpr (PERSIST) {
+            if (j + 2 == nt0) umma_commit(bar_qe);  // that was the item's last QK^T: the producer may fetch the next item's Q
+          }
+        }
         __syncwarp();
       }
       mbar_wait(bar_vf(s), ph);
@@ -333,6 +417,9 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int t = t_lo; t < t_hi; ++t) {
         if (j < stream_nt(t)) {
           mbar_wait(bar_p(t), (j + pb.strm(t)) & 1);
+          if constexpr (PERSIST) {
+            if (j == 0 && k > 0) mbar_wait(bar_d(t), (k - 1) & 1);  // PV(0) overwrites O_t: the previous item's epilogue must have read it
+          }
           tc_fence_after();
           if (elect_one()) {
             issue_pv(t, s, j > 0);
@@ -349,16 +436,27 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   if (warp < 4) {
     reg_dec<kRegsLow>();
-    if (warp == 0) producer(PbZero{}, true);
-    else if (warp == 1) mma_issuer(PbZero{}, 0, kDualIssue ? 1 : 2);
-    else if (warp == 2 && kDualIssue) mma_issuer(PbZero{}, 1, 2);
-    if constexpr (NOMAX) {
-      named_bar_sync(0, kThreads);  // the softmax warps have looked at the row sums of the unshifted pass
-      if (*redo_flag) {
-        const PbPass2 pb = pass2_bases();
-        if (warp == 0) producer(pb, false);
-        else if (warp == 1) mma_issuer(pb, 0, kDualIssue ? 1 : 2);
-        else if (warp == 2 && kDualIssue) mma_issuer(pb, 1, 2);
+    auto role = [&](auto pb, bool load_q, int k) {
+      if (warp == 0) producer(pb, load_q, k);
+      else if (warp == 1) mma_issuer(pb, 0, kDualIssue ? 1 : 2, k);
+      else if (warp == 2 && kDualIssue) mma_issuer(pb, 1, 2, k);
+    };
+    if constexpr (PERSIST) {
+      // the pipeline roles do not care which loop the softmax warps run: every item is the same sequence of barrier phases
+      int k = 0;
+      for (int e = 0; e < (NOMAX ? 2 : 1) * n_local; ++e) {
+        bool exact;
+        const int it = next_entry(e, exact);
+        if (it == -2) break;
+        if (it < 0 || !set_item(it)) continue;
+        role(seq_bases(k), true, k);
+        ++k;
+      }
+    } else {
+      role(PbZero{}, true, 0);
+      if constexpr (NOMAX) {
+        named_bar_sync(0, kThreads);  // the softmax warps have looked at the row sums of the unshifted pass
+        if (*redo_flag) role(pass2_bases(), false, 0);
       }
     }
   } else {
@@ -375,8 +473,14 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // BIAS variant, rows with a key bias: the scores are turned into t = s * scale_log2 + bias * log2(e) right after the load, so the
     // maximum sees the bias and everything downstream works with a unit scale
     const float* bias_row = nullptr;
-    if constexpr (BIAS) bias_row = a.rows.bias[b] >= 0 ? a.key_bias + (int64_t)a.rows.bias[b] * a.Nk : nullptr;
-    const float c2 = (BIAS && bias_row != nullptr) ? 1.f : a.scale_log2;
+    float c2 = a.scale_log2;
+    auto item_setup = [&]() {  // per item: the batch row decides whether a key bias applies
+      if constexpr (BIAS) {
+        bias_row = a.rows.bias[b] >= 0 ? a.key_bias + (int64_t)a.rows.bias[b] * a.Nk : nullptr;
+        c2 = bias_row != nullptr ? 1.f : a.scale_log2;
+      }
+    };
+    if constexpr (!PERSIST) item_setup();
     float m_used = -INFINITY, l = 0.f;
     float qn_max = INFINITY, m_floor = -INFINITY;  // stream-wide max |q_row| and min first-tile row maximum (scaled): the skip test
     float qn_row = 0.f;
@@ -408,7 +512,7 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // Turn protocol: exp sections alternate 0(0) 1(0) 0(1) 1(1) ...; stream 0 waits for stream 1's previous section, stream
     // 1 for stream 0's current one. In the split flavour stream 1 may be one step short (odd tile count): stream 0's last
     // grant then simply goes unused.
-    auto run_pass = [&](auto fast_tag, auto pb) {
+    auto run_pass = [&](auto fast_tag, auto pb, int k) {
       constexpr bool FAST = decltype(fast_tag)::value;
       constexpr bool ordered = !FAST || kFastOrdered;
       for (int j = 0; j < my_nt; ++j) {
@@ -418,7 +522,7 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         float kn_cur = 0.f;  // requested here, needed after the score load: its latency hides behind the barrier wait and tcgen05.ld
         if constexpr (skip_guard && !FAST) kn_cur = __ldg(a.knorm + ((int64_t)kb_tile * a.H + h) * a.knorm_tiles + jj);
 #if IEF_TC3_TRACE
-        const bool trace = a.dbg != nullptr && lin == 0 && row == 0 && half == 0 && j < 64;
+        const bool trace = cta_trace && k == IEF_TC3_TRACE_ITEM && row == 0 && half == 0 && j < 64;
         long long* tr = trace ? a.dbg + (t * 64 + j) * 8 : nullptr;
 #else
         constexpr bool trace = false;
@@ -546,7 +650,11 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (trace) tr[7] = clock64();
 #endif
         if constexpr (ordered) {
-          if (t == 1 || j > 0) mbar_wait(bar_x(t), ((t == 1 ? j : j - 1) + pb.turn(t)) & 1);   // ordered exp sections
+          // ordered exp sections. Persistent: stream 0's first section of an item follows stream 1's last section of the previous one
+          // (every grant is consumed, so no phase of a turn barrier can complete unobserved); stream 1 grants stream 0's very first
+          // section before its first item, so stream 0 waits for phase j like stream 1
+          if constexpr (PERSIST) mbar_wait(bar_x(t), j & 1);
+          else if (t == 1 || j > 0) mbar_wait(bar_x(t), ((t == 1 ? j : j - 1) + pb.turn(t)) & 1);
         }
         if (trace) tr[3] = clock64();
         float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
@@ -601,81 +709,136 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     };
 
-    float lrow;
-    if constexpr (NOMAX) {
-      m_used = 0.f;
-      run_pass(BoolTag<true>{}, PbZero{});
-      lrow = row_sum();
-      if (my_nt > 0 && !(lrow > kNoMaxLo && lrow < kNoMaxHi)) *redo_flag = 1;  // inf, NaN, zero or close to the edge of the fp32 / bf16 range
-      named_bar_sync(0, kThreads);
-      if (*redo_flag) {
-        m_used = -INFINITY;
-        l = 0.f;
-        run_pass(BoolTag<false>{}, pass2_bases());
-        lrow = row_sum();
-      }
-    } else {
-      run_pass(BoolTag<false>{}, PbZero{});
-      lrow = row_sum();
-    }
-    // ---- epilogue
-    const int nchunk_d = (a.d + 15) >> 4;
-    float wmine = 1.f, wother = 0.f;
-    if constexpr (SPLIT) {
-      // ... then the two key halves. When stream 1's last PV has completed, every QK MMA of the CTA has completed too
-      // (program order of the issuing thread), so the K ring is free to serve as staging; the V ring may still be in use.
-      if (t == 1 && nt1 > 0) {
-        if (half == 0) {
-          xml[row] = m_used;
-          xml[128 + row] = lrow;
+    // ---- epilogue of one item: merge (split flavour), normalise, store; persistent CTAs then hand O_t back to the issuer
+    auto epilogue = [&](float lrow) {
+      const int nchunk_d = (a.d + 15) >> 4;
+      float wmine = 1.f, wother = 0.f;
+      if constexpr (SPLIT) {
+        // ... then the two key halves. When stream 1's last PV has completed, every QK MMA of the CTA has completed too
+        // (program order of the issuing thread), so the K ring is free to serve as staging; the V ring may still be in use.
+        if (t == 1 && nt1 > 0) {
+          if (half == 0) {
+            xml[row] = m_used;
+            xml[128 + row] = lrow;
+          }
+          for (int cc = half; cc < nchunk_d; cc += 2) {
+            uint32_t r[16];
+            tmem_ld16(tO + 16 * cc, r);
+            tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) stage_o[(16 * cc + i) * 128 + row] = __uint_as_float(r[i]);
+          }
         }
+        named_bar_sync(3, 512);
+        if (t == 0 && nt1 > 0) {
+          const float mB = xml[row], lB = xml[128 + row];
+          const float m = fmaxf(m_used, mB);
+          wmine = ief_exp2((m_used - m) * c2);
+          wother = ief_exp2((mB - m) * c2);
+          lrow = lrow * wmine + lB * wother;
+        }
+      }
+      if (!SPLIT || t == 0) {
+        if (a.lse_out != nullptr && half == 0) {  // row log-sum-exp (log2 units) for the stored-maps sweep
+          const int r = (Cfg::kQTiles * qt + (SPLIT ? 0 : t)) * kBM + row;
+          // split flavour: lrow already is the merged sum relative to the joint maximum m_used + log2(1 / wmine) / c2
+          const float m_ref = (SPLIT && nt1 > 0) ? m_used * c2 - log2f(wmine) : m_used * c2;
+          if (r < a.Nq) a.lse_out[((int64_t)b * a.H + h) * a.Nq + r] = m_ref + log2f(lrow);
+        }
+        const float inv = 1.f / lrow;
+        wmine *= inv;
+        wother *= inv;
+        const int grow = (Cfg::kQTiles * qt + (SPLIT ? 0 : t)) * kBM + row;
+        typename E::T* op = reinterpret_cast<typename E::T*>(a.o) + (int64_t)b * a.o_sb + (int64_t)grow * a.o_sn + (int64_t)h * a.o_sh;
         for (int cc = half; cc < nchunk_d; cc += 2) {
           uint32_t r[16];
           tmem_ld16(tO + 16 * cc, r);
           tc_wait_ld();
+          float f[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) stage_o[(16 * cc + i) * 128 + row] = __uint_as_float(r[i]);
+          for (int i = 0; i < 16; ++i) {
+            f[i] = __uint_as_float(r[i]) * wmine;
+            if (SPLIT && nt1 > 0) f[i] = fmaf(stage_o[(16 * cc + i) * 128 + row], wother, f[i]);
+          }
+          if (grow < a.Nq) {
+            uint4 v0, v1;
+            v0.x = E::pack(f[0], f[1]); v0.y = E::pack(f[2], f[3]); v0.z = E::pack(f[4], f[5]); v0.w = E::pack(f[6], f[7]);
+            v1.x = E::pack(f[8], f[9]); v1.y = E::pack(f[10], f[11]); v1.z = E::pack(f[12], f[13]); v1.w = E::pack(f[14], f[15]);
+            if (16 * cc + 8 <= a.d) *reinterpret_cast<uint4*>(op + 16 * cc) = v0;
+            if (16 * cc + 16 <= a.d) *reinterpret_cast<uint4*>(op + 16 * cc + 8) = v1;
+          }
         }
       }
-      named_bar_sync(3, 512);
-      if (t == 0 && nt1 > 0) {
-        const float mB = xml[row], lB = xml[128 + row];
-        const float m = fmaxf(m_used, mB);
-        wmine = ief_exp2((m_used - m) * c2);
-        wother = ief_exp2((mB - m) * c2);
-        lrow = lrow * wmine + lB * wother;
+      if constexpr (PERSIST) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_d(t));
       }
-    }
-    if (!SPLIT || t == 0) {
-      if (a.lse_out != nullptr && half == 0) {  // row log-sum-exp (log2 units) for the stored-maps sweep
-        const int r = (Cfg::kQTiles * qt + (SPLIT ? 0 : t)) * kBM + row;
-        // split flavour: lrow already is the merged sum relative to the joint maximum m_used + log2(1 / wmine) / c2
-        const float m_ref = (SPLIT && nt1 > 0) ? m_used * c2 - log2f(wmine) : m_used * c2;
-        if (r < a.Nq) a.lse_out[((int64_t)b * a.H + h) * a.Nq + r] = m_ref + log2f(lrow);
+    };
+
+    if constexpr (PERSIST) {
+      if (t == 1) {  // stream 0's first exp section of the CTA has no predecessor: granted here
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_x(0));
       }
-      const float inv = 1.f / lrow;
-      wmine *= inv;
-      wother *= inv;
-      const int grow = (Cfg::kQTiles * qt + (SPLIT ? 0 : t)) * kBM + row;
-      typename E::T* op = reinterpret_cast<typename E::T*>(a.o) + (int64_t)b * a.o_sb + (int64_t)grow * a.o_sn + (int64_t)h * a.o_sh;
-      for (int cc = half; cc < nchunk_d; cc += 2) {
-        uint32_t r[16];
-        tmem_ld16(tO + 16 * cc, r);
-        tc_wait_ld();
-        float f[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          f[i] = __uint_as_float(r[i]) * wmine;
-          if (SPLIT && nt1 > 0) f[i] = fmaf(stage_o[(16 * cc + i) * 128 + row], wother, f[i]);
+      int k = 0;
+#pragma nounroll
+      for (int e = 0; e < (NOMAX ? 2 : 1) * n_local; ++e) {
+        bool exact;
+        int it = next_entry(e, exact);
+        if (it == -2) break;
+        if (it < 0 || !set_item(it)) continue;
+        item_setup();
+        l = 0.f;
+#if IEF_TC3_TRACE
+        long long* trk = cta_trace && row == 0 && half == 0 && k < 16 ? a.dbg + 1600 + (k * 2 + t) * 4 : nullptr;  // item start | loop end | epilogue end
+        if (trk) trk[0] = clock64();
+#endif
+        if constexpr (NOMAX) {
+          if (!exact) {
+            m_used = 0.f;
+            run_pass(BoolTag<true>{}, seq_bases(k), k);
+          }
         }
-        if (grow < a.Nq) {
-          uint4 v0, v1;
-          v0.x = E::pack(f[0], f[1]); v0.y = E::pack(f[2], f[3]); v0.z = E::pack(f[4], f[5]); v0.w = E::pack(f[6], f[7]);
-          v1.x = E::pack(f[8], f[9]); v1.y = E::pack(f[10], f[11]); v1.z = E::pack(f[12], f[13]); v1.w = E::pack(f[14], f[15]);
-          if (16 * cc + 8 <= a.d) *reinterpret_cast<uint4*>(op + 16 * cc) = v0;
-          if (16 * cc + 16 <= a.d) *reinterpret_cast<uint4*>(op + 16 * cc + 8) = v1;
+        if (exact) {
+          m_used = -INFINITY;
+          run_pass(BoolTag<false>{}, seq_bases(k), k);
         }
+#if IEF_TC3_TRACE
+        if (trk) trk[1] = clock64();
+#endif
+        const float lrow = row_sum();
+        if constexpr (NOMAX) {  // inf, NaN, zero or close to the edge of the fp32 / bf16 range: flag the item for the exact sweep
+          if (!exact && !(lrow > kNoMaxLo && lrow < kNoMaxHi)) atomicOr(const_cast<uint32_t*>(redo_flag), 1u << it);
+        }
+        // the item's coordinates are recomputed here instead of being carried through the key loop in registers
+        asm volatile("" : "+r"(it));
+        set_item(it);
+        epilogue(lrow);
+#if IEF_TC3_TRACE
+        if (trk) trk[2] = clock64();
+#endif
+        ++k;
       }
+    } else {
+      float lrow;
+      if constexpr (NOMAX) {
+        m_used = 0.f;
+        run_pass(BoolTag<true>{}, PbZero{}, 0);
+        lrow = row_sum();
+        if (my_nt > 0 && !(lrow > kNoMaxLo && lrow < kNoMaxHi)) *redo_flag = 1;  // inf, NaN, zero or close to the edge of the fp32 / bf16 range
+        named_bar_sync(0, kThreads);
+        if (*redo_flag) {
+          m_used = -INFINITY;
+          l = 0.f;
+          run_pass(BoolTag<false>{}, pass2_bases(), 0);
+          lrow = row_sum();
+        }
+      } else {
+        run_pass(BoolTag<false>{}, PbZero{}, 0);
+        lrow = row_sum();
+      }
+      epilogue(lrow);
     }
   }
   if (cta_trace && warp == 4 && lane == 0) a.dbg[1540] = clock64();
@@ -688,16 +851,31 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (cta_trace && threadIdx.x == 32) a.dbg[1541] = clock64();
 }
 
+template <int DTYPE, bool SPLIT, bool SUMMMA, int MAXMODE, bool BIAS, bool PERSIST>
+int launch_tc3k(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const TcArgs& a, int grid, cudaStream_t st) {
+  auto kern = attn_tc3_kernel<DTYPE, SPLIT, kDefaultEmul, SUMMMA, MAXMODE, BIAS, PERSIST>;
+  IEF_CONFIG_SMEM(kern, Cfg3<SPLIT>::kSmemBytes);
+  kern<<<grid, kThreads, Cfg3<SPLIT>::kSmemBytes, st>>>(mq, mk, mv, a);
+  IEF_LAUNCH_OK("attn_tc3_kernel");
+  return IEF_OK;
+}
+
 template <int DTYPE, bool SPLIT, bool SUMMMA, int MAXMODE, bool BIAS = false>
 int launch_tc3s(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, TcArgs a, int first, int count, int nq_blocks, cudaStream_t st) {
-  auto kern = attn_tc3_kernel<DTYPE, SPLIT, kDefaultEmul, SUMMMA, MAXMODE, BIAS>;
-  IEF_CONFIG_SMEM(kern, Cfg3<SPLIT>::kSmemBytes);
   if (count <= 0) return IEF_OK;
   a.work_offset = first;
   a.nq_blocks = nq_blocks;
-  kern<<<count, kThreads, Cfg3<SPLIT>::kSmemBytes, st>>>(mq, mk, mv, a);
-  IEF_LAUNCH_OK("attn_tc3_kernel");
-  return IEF_OK;
+  a.n_items = count;
+  // Persistent form (one CTA per SM walks count / #SM items): 256-row flavour with more items than SMs and an even number of key
+  // tiles per item (see the kernel); everything else runs one item per CTA
+  if constexpr (kPersist && !SPLIT && MAXMODE != 1 && kFastOrdered) {
+    const int sms = ief_sm_count();
+    if (count > sms && ((a.nt1 + a.nt2) & 1) == 0) {
+      const int grid = sms * kMaxItemsPerCta >= count ? sms : ief_ceil_div(count, kMaxItemsPerCta);
+      return launch_tc3k<DTYPE, SPLIT, SUMMMA, MAXMODE, BIAS, true>(mq, mk, mv, a, grid, st);
+    }
+  }
+  return launch_tc3k<DTYPE, SPLIT, SUMMMA, MAXMODE, BIAS, false>(mq, mk, mv, a, count, st);
 }
 
 template <int DTYPE, bool SPLIT>

@@ -43,3 +43,15 @@ c = t[1536:1542]
 if int(c[0]) != 0:
     k0 = int(c[0])
     print(f"CTA: setup {int(c[1]) - k0}, first tile start {t0 - k0}, first S ready {int(sm[0, 0, 1]) - k0}, loop end {int(c[2]) - k0}, last PV {int(c[3]) - k0}, epilogue {int(c[4]) - k0}, exit {int(c[5]) - k0}")
+it = t[1600:1728].view(16, 2, 4)
+if int(it[0, 0, 0]) != 0:
+    print("persistent CTA 0, per item and stream: start | loop end (last PV done) | epilogue end   [cycles since CTA start; item length = start-to-start]")
+    for k_ in range(16):
+        if int(it[k_, 0, 0]) == 0:
+            break
+        row_ = []
+        for s_ in range(2):
+            a0, a1, a2 = (int(x) - int(c[0]) for x in it[k_, s_, :3])
+            nxt = int(it[k_ + 1, s_, 0]) - int(c[0]) if k_ + 1 < 16 and int(it[k_ + 1, s_, 0]) != 0 else None
+            row_.append(f"t{s_}: {a0:7d} {a1:7d} {a2:7d} (loop {a1 - a0}, epilogue {a2 - a1}" + (f", to next start {nxt - a2}, item {nxt - a0})" if nxt is not None else ")"))
+        print(f"  item {k_:2d} | " + " | ".join(row_))
