@@ -460,14 +460,19 @@ int ief_attn_tc_launch(const ief_attn_params* p, const IefRowTable& rows, cudaSt
       force = e ? atoi(e) : -1;
     }
     const int sms = ief_sm_count();
-    // estimated time in units of one key step (~2.25 K cycles): waves x (steps per CTA + fixed cost). Measured fixed costs (tools/tc3_trace.py):
-    // ~8.5 K cycles = 4 steps per pair CTA, one more for a split-KV CTA's merge, and ~3 steps for the gap before a second launch
+    // estimated time in half key steps (one step ~2.25 K cycles). Measured costs (tools/tc3_trace.py, profiles/r02_attn_tc3_persistent.txt):
+    // a one-item 256-row CTA pays ~4 steps of prologue + epilogue, an item of a persistent CTA ~1.5 (+2.5 once per launch), a split-KV
+    // CTA one more than a pair CTA for its merge, and a second launch ~3.5 steps (gap + cold start)
     const int nt = a.nt1 + a.nt2;
     const long pairs = (long)ief_ceil_div(p->Nq, 2 * kBM) * p->H * p->B;
     const long full = pairs / sms, rest = pairs % sms;
-    const long t_pair = (full + (rest ? 1 : 0)) * (nt + 4);
-    const long t_split = ((2 * pairs + sms - 1) / sms) * ((nt + 1) / 2 + 5);
-    const long t_hybrid = full * (nt + 4) + ((2 * rest + sms - 1) / sms) * ((nt + 1) / 2 + 5) + (rest ? 3 : 0);
+    auto pair_cost = [&](long waves, long items) {  // `items` 256-row items spread over the SMs in `waves` rounds
+      return ief_attn_tc3_persistent(items, nt) ? waves * (2 * nt + 3) + 5 : waves * (2 * nt + 8);
+    };
+    const long split_wave = 2 * ((nt + 1) / 2) + 10;
+    const long t_pair = pair_cost(full + (rest ? 1 : 0), pairs);
+    const long t_split = ((2 * pairs + sms - 1) / sms) * split_wave;
+    const long t_hybrid = pair_cost(full, full * sms) + ((2 * rest + sms - 1) / sms) * split_wave + (rest ? 7 : 0);
     int mode = 0;  // 0 pair, 1 split, 2 hybrid
     if (force >= 0) mode = force;
     else if (t_hybrid < t_pair && t_hybrid <= t_split && full > 0 && rest > 0) mode = 2;

@@ -46,6 +46,7 @@
 #include "attn_tc_host.cuh"
 #include "attn_tc_dev.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 using namespace sm100;
 
@@ -82,7 +83,10 @@ constexpr int kSmemXchg = 8 * 1024;            // floats: row-max exchange [2 pa
 #ifndef IEF_TC3_EMUL
 #define IEF_TC3_EMUL 4
 #endif
-constexpr int kDefaultEmul = IEF_TC3_EMUL;
+#ifndef IEF_TC3_EMUL_D64
+#define IEF_TC3_EMUL_D64 IEF_TC3_EMUL  // the same share for head_dim 49-64 (row sums in registers: the FMA pipe is busier there)
+#endif
+template <bool SUMMMA> constexpr int kDefaultEmul = SUMMMA ? IEF_TC3_EMUL : IEF_TC3_EMUL_D64;
 constexpr float kRescaleThreshold = 8.0f;
 // bf16 only: a tile whose Cauchy-Schwarz score bound stays within 2^kSkipMargin of the first tile's smallest row maximum needs no
 // row-maximum pass at all (P and the fp32 accumulators have 8 exponent bits; see the softmax section)
@@ -92,8 +96,23 @@ constexpr float kNoMaxLo = 7.8886090522101181e-31f, kNoMaxHi = 1.267650600228229
 #ifndef IEF_TC3_FAST_ORDERED
 #define IEF_TC3_FAST_ORDERED 1     // 0: the unshifted loop runs its exp sections unordered (A/B)
 #endif
+// Two switches of the unshifted loop, per accumulator layout (measured on the persistent form, profiles/r02_attn_tc3_persistent.txt):
+//   scale inside the exp section instead of in front of the turn   head_dim <= 48: -1 %      49-64: +1-2 %
+//   wait for PV_t(j-1) right before the first store of P (half an exp section into the turn) instead of in front of the turn
+//                                                                   head_dim <= 48: +2.5 %    49-64: -6 %
+// (head_dim 49-64 sums its rows in registers: ~340 instructions per thread and tile inside the exp section against ~240, its
+// sections are bound by instruction issue as much as by the MUFU — with NO exponential on the FMA pipe it runs at the same speed)
 #ifndef IEF_TC3_FAST_SCALE_IN_TURN
-#define IEF_TC3_FAST_SCALE_IN_TURN 0  // 1: the scale multiply rides inside the exp section instead of before the turn (A/B)
+#define IEF_TC3_FAST_SCALE_IN_TURN 0
+#endif
+#ifndef IEF_TC3_FAST_SCALE_IN_TURN_D64
+#define IEF_TC3_FAST_SCALE_IN_TURN_D64 1
+#endif
+#ifndef IEF_TC3_PV_WAIT_LATE
+#define IEF_TC3_PV_WAIT_LATE 1
+#endif
+#ifndef IEF_TC3_PV_WAIT_LATE_D64
+#define IEF_TC3_PV_WAIT_LATE_D64 0
 #endif
 constexpr bool kFastOrdered = IEF_TC3_FAST_ORDERED != 0;
 // Two tcgen05.mma issuer warps, one per stream (warp 1: stream 0, warp 2: stream 1), instead of one warp walking QK_0 QK_1 PV_0 PV_1 in
@@ -203,7 +222,7 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   float* xq = xml + 256;                                   // [2 streams][8 warps][2]: one-time (max |q|, min row max) exchange
   uint32_t bar0_ = base + Cfg::kSmemData + kSmemOnes + kSmemXchg;
 #if IEF_TC3_PIN_BAR0
-  if constexpr (PERSIST) asm volatile("" : "+r"(bar0_));  // one register instead of re-deriving the shared-memory window address inside the key loop
+  if constexpr (PERSIST || IEF_TC3_PIN_BAR0 >= 2) asm volatile("" : "+r"(bar0_));  // one register instead of re-deriving the shared-memory window address inside the key loop
 #endif
   const uint32_t bar0 = bar0_;
   const uint32_t bar_q = bar0;
@@ -634,7 +653,7 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #endif
         const float mc = FAST ? 0.f : m_used * c2;
         const float2 c2v = make_float2(c2, c2), nmc = make_float2(-mc, -mc);
-        constexpr bool scale_in_turn = FAST && IEF_TC3_FAST_SCALE_IN_TURN;
+        constexpr bool scale_in_turn = FAST && (SUMMMA ? IEF_TC3_FAST_SCALE_IN_TURN : IEF_TC3_FAST_SCALE_IN_TURN_D64);
         if constexpr (!scale_in_turn) {
           scale_chunk_mix<EMUL>(s0, c2v, nmc);   // FMA-pipe work (incl. the emulated share of the exponentials), outside the MUFU turn
           scale_chunk_mix<EMUL>(s1, c2v, nmc);
@@ -642,7 +661,8 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #if IEF_TC3_FINE_TRACE
         if (trace) tr[6] = clock64();
 #endif
-        if (!o_ready) {  // PV_t(j-1) must have finished reading P_t; wait for it BEFORE taking the exp turn, not inside it
+        constexpr bool pv_wait_late = (SUMMMA ? IEF_TC3_PV_WAIT_LATE : IEF_TC3_PV_WAIT_LATE_D64) != 0;
+        if (!o_ready && !(FAST && pv_wait_late)) {  // PV_t(j-1) must have finished reading P_t; wait for it BEFORE taking the exp turn, not inside it
           mbar_wait(bar_o(t), (j - 1 + pb.strm(t)) & 1);
           tc_fence_after();
         }
@@ -661,6 +681,14 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         uint32_t u[16];
         if constexpr (scale_in_turn) scale_chunk_mix<EMUL>(s0, c2v, nmc);
         if constexpr (sum_mma) exp_pack_chunk_nosum<E, EMUL>(s0, u); else exp_pack_chunk_mix<E, EMUL>(s0, u, acc0, acc1);
+        if constexpr (FAST && pv_wait_late) {
+          // unshifted loop: only the first store of P needs PV_t(j-1) to have read the previous P_t; by now (half an exp section into
+          // the turn) it practically always has, so the wait costs one barrier poll instead of ~200 cycles in front of the turn
+          if (!o_ready) {
+            mbar_wait(bar_o(t), (j - 1 + pb.strm(t)) & 1);
+            tc_fence_after();
+          }
+        }
         tmem_st16(tP, u);
 #if !IEF_TC3_HANDOVER_LATE
         if constexpr (ordered) {
@@ -853,7 +881,7 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
 template <int DTYPE, bool SPLIT, bool SUMMMA, int MAXMODE, bool BIAS, bool PERSIST>
 int launch_tc3k(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const TcArgs& a, int grid, cudaStream_t st) {
-  auto kern = attn_tc3_kernel<DTYPE, SPLIT, kDefaultEmul, SUMMMA, MAXMODE, BIAS, PERSIST>;
+  auto kern = attn_tc3_kernel<DTYPE, SPLIT, kDefaultEmul<SUMMMA>, SUMMMA, MAXMODE, BIAS, PERSIST>;
   IEF_CONFIG_SMEM(kern, Cfg3<SPLIT>::kSmemBytes);
   kern<<<grid, kThreads, Cfg3<SPLIT>::kSmemBytes, st>>>(mq, mk, mv, a);
   IEF_LAUNCH_OK("attn_tc3_kernel");
@@ -868,9 +896,9 @@ int launch_tc3s(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap&
   a.n_items = count;
   // Persistent form (one CTA per SM walks count / #SM items): 256-row flavour with more items than SMs and an even number of key
   // tiles per item (see the kernel); everything else runs one item per CTA
-  if constexpr (kPersist && !SPLIT && MAXMODE != 1 && kFastOrdered) {
-    const int sms = ief_sm_count();
-    if (count > sms && ((a.nt1 + a.nt2) & 1) == 0) {
+  if constexpr (!SPLIT && MAXMODE != 1) {
+    if (ief_attn_tc3_persistent(count, a.nt1 + a.nt2)) {
+      const int sms = ief_sm_count();
       const int grid = sms * kMaxItemsPerCta >= count ? sms : ief_ceil_div(count, kMaxItemsPerCta);
       return launch_tc3k<DTYPE, SPLIT, SUMMMA, MAXMODE, BIAS, true>(mq, mk, mv, a, grid, st);
     }
@@ -904,12 +932,16 @@ int launch_mode(const ief_attn_params* p, const CUtensorMap& mq, const CUtensorM
   // hybrid: the full waves as 256-row CTAs, the remaining r < #SM/2 pairs as 2r half-length split-KV CTAs (pair L = split 2L, 2L+1)
   const int sms = ief_sm_count();
   const int full = (pairs / sms) * sms, rest = pairs - full;
-  int rc = launch_tc3<DTYPE, false>(mq, mk, mv, a, 0, full, nqp, st);
-  if (rc != IEF_OK) return rc;
+  static int diag_part = -1;  // IEF_TC3_DIAG_PART=1|2: launch only the full waves / only the remainder (WRONG results; timing of the two parts)
+  if (diag_part < 0) { const char* e = getenv("IEF_TC3_DIAG_PART"); diag_part = e ? atoi(e) : 0; }
+  int rc = diag_part == 2 ? IEF_OK : launch_tc3<DTYPE, false>(mq, mk, mv, a, 0, full, nqp, st);
+  if (rc != IEF_OK || diag_part == 1) return rc;
   return launch_tc3<DTYPE, true>(mq, mk, mv, a, 2 * full, 2 * rest, 2 * nqp, st);
 }
 
 }  // namespace
+
+bool ief_attn_tc3_persistent(long items, int nt) { return kPersist && kFastOrdered && items > ief_sm_count() && (nt & 1) == 0; }
 
 int ief_attn_tc3_launch(const ief_attn_params* p, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const TcArgs& a, int mode,
                         cudaStream_t st) {

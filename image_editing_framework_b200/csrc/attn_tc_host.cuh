@@ -41,4 +41,5 @@ long long* ief_debug_trace_buffer();
 int ief_tc_make_map(CUtensorMap* m, int dtype, const ief_tensor4& t, int d, int N, int H, int B, int32_t perm[3], int box_rows);
 int ief_attn_tc3_launch(const ief_attn_params* p, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const TcArgs& a, int mode,
                         cudaStream_t st);  // mode: 0 pair, 1 split, 2 hybrid (full waves as pairs, remainder split)
+bool ief_attn_tc3_persistent(long items, int nt);  // would a 256-row launch of `items` items with nt key tiles each run as persistent CTAs?
 int ief_attn_tc2_launch(const ief_attn_params* p, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const TcArgs& a, cudaStream_t st);
