@@ -195,10 +195,14 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   // a persistent CTA takes the items blockIdx.x, blockIdx.x + gridDim.x, ... of the launch's n_items
   int qt, h, b;  // 256-row block (pair) or 128-row tile (split), head, batch row of the current item: every thread walks the same sequence
   auto set_item = [&](int it) -> bool {
-    const int lin = a.work_offset + (int)blockIdx.x + it * (int)gridDim.x;
-    qt = lin % a.nq_blocks;
-    h = (lin / a.nq_blocks) % a.H;
-    b = lin / (a.nq_blocks * a.H);
+    // division by the two launch constants through host-made reciprocals (exact for lin * divisor < 2^32, checked by the launcher):
+    // this runs on the softmax warps between two items, next to the other stream's exp section
+    const uint32_t lin = (uint32_t)(a.work_offset + (int)blockIdx.x + it * (int)gridDim.x);
+    const uint32_t bb = (uint32_t)(((uint64_t)lin * a.rcp_nq_h) >> 32), rem = lin - bb * (uint32_t)(a.nq_blocks * a.H);
+    const uint32_t hh = (uint32_t)(((uint64_t)rem * a.rcp_nq) >> 32);
+    b = (int)bb;
+    h = (int)hh;
+    qt = (int)(rem - hh * (uint32_t)a.nq_blocks);
     return a.rows.active[b] != 0;
   };
   const int n_local = PERSIST ? (a.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 1;
@@ -894,6 +898,11 @@ int launch_tc3s(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap&
   a.work_offset = first;
   a.nq_blocks = nq_blocks;
   a.n_items = count;
+  // ceil(2^32 / divisor): floor(lin * rcp / 2^32) == lin / divisor for every lin < 2^32 / divisor
+  const uint64_t div_h = (uint64_t)nq_blocks * (uint64_t)a.H, last = (uint64_t)first + (uint64_t)count;
+  IEF_REQUIRE(last * div_h < (1ull << 32), IEF_ERR_UNSUPPORTED, "tcgen05 attention: %llu work items exceed the kernel's index arithmetic", (unsigned long long)last);
+  a.rcp_nq = ((1ull << 32) + (uint64_t)nq_blocks - 1) / (uint64_t)nq_blocks;
+  a.rcp_nq_h = ((1ull << 32) + div_h - 1) / div_h;
   // Persistent form (one CTA per SM walks count / #SM items): 256-row flavour with more items than SMs and an even number of key
   // tiles per item (see the kernel); everything else runs one item per CTA
   if constexpr (!SPLIT && MAXMODE != 1) {
