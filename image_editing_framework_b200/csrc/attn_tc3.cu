@@ -72,6 +72,12 @@ constexpr int kSmemXchg = 8 * 1024;            // floats: row-max exchange [2 pa
 #ifndef IEF_TC3_TRACE_ITEM
 #define IEF_TC3_TRACE_ITEM 0  // which of a persistent CTA's items gets the per-tile stamps
 #endif
+#ifndef IEF_TC3_LD64
+#define IEF_TC3_LD64 0  // experiment: the 64 score columns of a thread in one tcgen05.ld.x64 instead of two x32
+#endif
+#ifndef IEF_TC3_HANDOVER_EARLY
+#define IEF_TC3_HANDOVER_EARLY 0  // experiment: hand the turn over on entering the exp section
+#endif
 #ifndef IEF_TC3_HANDOVER_LATE
 #define IEF_TC3_HANDOVER_LATE 0  // experiment: hand the turn over after the whole exp section instead of one chunk early
 #endif
@@ -559,8 +565,12 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tc_fence_after();
         if (trace) tr[1] = clock64();
         uint32_t s0[32], s1[32];
+#if IEF_TC3_LD64
+        tmem_ld64(tS, s0, s1);
+#else
         tmem_ld32(tS, s0);
         tmem_ld32(tS + 32, s1);
+#endif
         tc_wait_ld();
         tc_fence_before();
         __syncwarp();
@@ -681,6 +691,12 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           else if (t == 1 || j > 0) mbar_wait(bar_x(t), ((t == 1 ? j : j - 1) + pb.turn(t)) & 1);
         }
         if (trace) tr[3] = clock64();
+#if IEF_TC3_HANDOVER_EARLY
+        if constexpr (ordered) {  // experiment: the other stream may start as soon as this one HAS started (sections only staggered)
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_x(t ^ 1));
+        }
+#endif
         float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
         uint32_t u[16];
         if constexpr (scale_in_turn) scale_chunk_mix<EMUL>(s0, c2v, nmc);
@@ -694,7 +710,7 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
         }
         tmem_st16(tP, u);
-#if !IEF_TC3_HANDOVER_LATE
+#if !IEF_TC3_HANDOVER_LATE && !IEF_TC3_HANDOVER_EARLY
         if constexpr (ordered) {
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_x(t ^ 1));  // hand the MUFU over one chunk early

@@ -160,6 +160,7 @@ def test_attn_tcgen05_max_skipping_guard(cuda, case):
     (2, 2, 640, 1100, 40),     # split-KV, odd number of key tiles (stream 1 one step short), row-sum MMA
     (2, 8, 2560, 1024, 40),    # 256-row pair CTAs (+ hybrid remainder), row-sum MMA
     (2, 10, 2304, 2304, 64),   # pair CTAs, row sums in registers
+    (2, 10, 4096, 1024, 64),   # persistent pair CTAs (320 items on 148 SMs: up to three per CTA, flagged ones repeated last), row sums in registers
 ])
 @pytest.mark.parametrize("case", ["plain", "overflow", "underflow", "one_batch_row", "few_query_rows", "union"])
 def test_attn_tcgen05_unshifted_softmax_second_pass(cuda, shape, case):
@@ -191,6 +192,31 @@ def test_attn_tcgen05_unshifted_softmax_second_pass(cuda, shape, case):
     assert torch.isfinite(got).all(), f"{case}: non-finite output"
     err = (got.float().cpu() - want).abs().max().item()
     assert err < TOL, f"{case} {shape}: max abs err {err}"
+
+
+@pytest.mark.parametrize("d", [40, 64])
+def test_attn_tcgen05_persistent_ctas_with_masked_rows(cuda, d):
+    """More 256-row work items than SMs and an even number of key tiles: one CTA per SM walks several items (attn_tc3, PERSIST).
+    Batch rows left out with `rows=` are skipped by every role of a CTA alike, rows of `out` that are not computed stay untouched,
+    and an overflowing batch row between clean ones sends only its own items through the exact repeat after the CTA's last item."""
+    B, H, N, M = 6, 8, 2048, 1024
+    q, k, v = _qkv(B, N, M, H, d, 77 + d)
+    q, k = q.float(), k.float()
+    q[4], k[4] = q[4] * 7, k[4] * 7          # row 4: unshifted row sums overflow
+    q, k = q.to(torch.bfloat16), k.to(torch.bfloat16)
+    src = [0, 0, 2, 2, 4, 4]                  # MasaCtrl-style: odd rows read the K, V of the even row before them
+    scale = d ** -0.5
+    want = orc.indexed_attention(q, k, v, H, scale, k_src=src, v_src=src)
+    rows = [0, 1, 3, 4, 5]
+    out = torch.full((B, N, H * d), 123.0, dtype=torch.bfloat16, device=cuda)
+    got = ops.attention(q.to(cuda), k.to(cuda), v.to(cuda), H, scale, impl=ops.IEF_IMPL_TCGEN05, k_src=src, v_src=src, rows=rows, out=out)
+    torch.cuda.synchronize()
+    assert _cabi.last_attn_impl() == "tcgen05"
+    got = got.float().cpu()
+    assert torch.isfinite(got).all()
+    assert (got[2] == 123.0).all(), "a row outside `rows` was written"
+    err = (got[rows] - want[rows]).abs().max().item()
+    assert err < TOL, f"max abs err {err}"
 
 
 def test_attn_auto_dispatch(cuda):
