@@ -966,7 +966,11 @@ int launch_mode(const ief_attn_params* p, const CUtensorMap& mq, const CUtensorM
 
 }  // namespace
 
-bool ief_attn_tc3_persistent(long items, int nt) { return kPersist && kFastOrdered && items > ief_sm_count() && (nt & 1) == 0; }
+bool ief_attn_tc3_persistent(long items, int nt) {
+  static int env = -1;  // IEF_TC3_PERSIST=0: one item per CTA everywhere (A/B switch read once; nothing device-dependent is cached)
+  if (env < 0) { const char* e = getenv("IEF_TC3_PERSIST"); env = (e && e[0] == '0') ? 0 : 1; }
+  return kPersist && kFastOrdered && env && items > ief_sm_count() && (nt & 1) == 0;
+}
 
 int ief_attn_tc3_launch(const ief_attn_params* p, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const TcArgs& a, int mode,
                         cudaStream_t st) {

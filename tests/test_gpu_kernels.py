@@ -194,21 +194,23 @@ def test_attn_tcgen05_unshifted_softmax_second_pass(cuda, shape, case):
     assert err < TOL, f"{case} {shape}: max abs err {err}"
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("d", [40, 64])
-def test_attn_tcgen05_persistent_ctas_with_masked_rows(cuda, d):
+def test_attn_tcgen05_persistent_ctas_with_masked_rows(cuda, d, dtype):
     """More 256-row work items than SMs and an even number of key tiles: one CTA per SM walks several items (attn_tc3, PERSIST).
     Batch rows left out with `rows=` are skipped by every role of a CTA alike, rows of `out` that are not computed stay untouched,
-    and an overflowing batch row between clean ones sends only its own items through the exact repeat after the CTA's last item."""
+    and an overflowing batch row between clean ones sends only its own items through the exact repeat after the CTA's last item
+    (bf16; fp16 runs the exact loop on every item)."""
     B, H, N, M = 6, 8, 2048, 1024
     q, k, v = _qkv(B, N, M, H, d, 77 + d)
     q, k = q.float(), k.float()
     q[4], k[4] = q[4] * 7, k[4] * 7          # row 4: unshifted row sums overflow
-    q, k = q.to(torch.bfloat16), k.to(torch.bfloat16)
+    q, k, v = q.to(dtype), k.to(dtype), v.to(dtype)
     src = [0, 0, 2, 2, 4, 4]                  # MasaCtrl-style: odd rows read the K, V of the even row before them
     scale = d ** -0.5
     want = orc.indexed_attention(q, k, v, H, scale, k_src=src, v_src=src)
     rows = [0, 1, 3, 4, 5]
-    out = torch.full((B, N, H * d), 123.0, dtype=torch.bfloat16, device=cuda)
+    out = torch.full((B, N, H * d), 123.0, dtype=dtype, device=cuda)
     got = ops.attention(q.to(cuda), k.to(cuda), v.to(cuda), H, scale, impl=ops.IEF_IMPL_TCGEN05, k_src=src, v_src=src, rows=rows, out=out)
     torch.cuda.synchronize()
     assert _cabi.last_attn_impl() == "tcgen05"

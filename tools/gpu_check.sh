@@ -11,6 +11,7 @@ IEF_TC_VERSION=2 run tc_v2 "tcgen05 or fp16 or row_sources or masactrl or lazy o
 IEF_TC_SPLITKV=1 run tc_v3_split "tcgen05 or fp16 or row_sources or masactrl or lazy or strided"
 IEF_TC_SPLITKV=2 run tc_v3_hybrid "tcgen05 or fp16 or row_sources or masactrl or lazy or strided"
 IEF_TC_SPLITKV=0 run tc_v3_pair "tcgen05 or fp16 or row_sources or masactrl or lazy or strided"
+IEF_TC3_PERSIST=0 run tc_v3_one_item_per_cta "tcgen05 or fp16 or row_sources or masactrl or lazy or strided"
 IEF_TC_VERSION=1 run tc_v1 "tcgen05 or fp16 or row_sources or masactrl or lazy or strided"
 IEF_TC3_NO_SUM_MMA=1 run tc_v3_no_summma "tcgen05 or fp16 or row_sources or masactrl or lazy or strided"
 IEF_TC3_SKIPMAX=2 run tc_v3_skip_everywhere "tcgen05 or fp16 or row_sources or masactrl or lazy or strided"
@@ -32,6 +33,7 @@ IEF_TC_SPLITKV=0 fuzz v3_pair
 IEF_TC_SPLITKV=1 fuzz v3_split
 IEF_TC3_SKIPMAX=2 fuzz skip_everywhere
 IEF_TC3_NOMAX=0 fuzz exact_only
+IEF_TC3_PERSIST=0 fuzz one_item_per_cta
 IEF_PROBS_VIA_LSE=0 fuzz probs_two_sweep
 IEF_CROSS_TC_EDIT=0 fuzz cross_edit_on_mma
 IEF_CROSS_TC_ONE_LAUNCH=0 fuzz cross_edit_two_launches
