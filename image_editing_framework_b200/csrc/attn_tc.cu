@@ -425,6 +425,7 @@ int ief_attn_tc_launch(const ief_attn_params* p, const IefRowTable& rows, cudaSt
   a.idesc_sum = make_idesc_f16(kBM, 16, fmt, 0, 0);
   a.knorm = nullptr;
   a.knorm_tiles = 0;
+  a.pdl = 0;
   a.lse_out = lse_out;
   a.key_bias = nullptr;
   for (int i = 0; i < p->B; ++i)

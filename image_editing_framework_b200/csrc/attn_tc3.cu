@@ -215,6 +215,10 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if constexpr (!PERSIST) {
     if (!set_item(0)) return;
   }
+  // The two launches of a hybrid call (full waves | remainder) read the same inputs and write disjoint rows: the remainder is launched
+  // as a programmatic dependent, so its CTAs move onto an SM as soon as that SM's CTA of this launch has left instead of after the
+  // whole grid has drained and a launch gap (nothing here is consumed by the dependent: the trigger can be given at once).
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const bool cta_trace = a.dbg != nullptr && blockIdx.x + a.work_offset == 0;
   if (cta_trace && threadIdx.x == 0) a.dbg[1536] = clock64();
 
@@ -890,6 +894,8 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
   }
   if (cta_trace && warp == 4 && lane == 0) a.dbg[1540] = clock64();
+  // a dependent launch must not COMPLETE before the launch it depends on: what follows in the stream waits for this grid only
+  if (a.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -903,7 +909,21 @@ template <int DTYPE, bool SPLIT, bool SUMMMA, int MAXMODE, bool BIAS, bool PERSI
 int launch_tc3k(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const TcArgs& a, int grid, cudaStream_t st) {
   auto kern = attn_tc3_kernel<DTYPE, SPLIT, kDefaultEmul<SUMMMA>, SUMMMA, MAXMODE, BIAS, PERSIST>;
   IEF_CONFIG_SMEM(kern, Cfg3<SPLIT>::kSmemBytes);
-  kern<<<grid, kThreads, Cfg3<SPLIT>::kSmemBytes, st>>>(mq, mk, mv, a);
+  if (a.pdl) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = Cfg3<SPLIT>::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    IEF_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, mq, mk, mv, a));
+  } else {
+    kern<<<grid, kThreads, Cfg3<SPLIT>::kSmemBytes, st>>>(mq, mk, mv, a);
+  }
   IEF_LAUNCH_OK("attn_tc3_kernel");
   return IEF_OK;
 }
@@ -961,7 +981,11 @@ int launch_mode(const ief_attn_params* p, const CUtensorMap& mq, const CUtensorM
   if (diag_part < 0) { const char* e = getenv("IEF_TC3_DIAG_PART"); diag_part = e ? atoi(e) : 0; }
   int rc = diag_part == 2 ? IEF_OK : launch_tc3<DTYPE, false>(mq, mk, mv, a, 0, full, nqp, st);
   if (rc != IEF_OK || diag_part == 1) return rc;
-  return launch_tc3<DTYPE, true>(mq, mk, mv, a, 2 * full, 2 * rest, 2 * nqp, st);
+  static int env_pdl = -1;  // IEF_TC3_PDL=0: the remainder as an ordinary second launch (A/B)
+  if (env_pdl < 0) { const char* e = getenv("IEF_TC3_PDL"); env_pdl = (e && e[0] == '0') ? 0 : 1; }
+  TcArgs a2 = a;
+  a2.pdl = (env_pdl && full > 0 && diag_part == 0) ? 1 : 0;
+  return launch_tc3<DTYPE, true>(mq, mk, mv, a2, 2 * full, 2 * rest, 2 * nqp, st);
 }
 
 }  // namespace
