@@ -41,6 +41,10 @@
 //           waits between two exp sections of a stream (~1300-1500 clk against a 1024 clk exp section of the other stream) -
 //           shrinks to load S -> scale -> waits.
 // (the same switches as run-time branches inside one loop cost 8-13 %: the fast and the exact loop are separate instantiations.)
+//
+// Launch forms (generation 3e): 256-row CTAs run PERSISTENT when a launch has more items than SMs (kPersist below: the next item's Q
+// load, first QK^T and exp turn overlap the epilogue of the current one); the remainder of a hybrid call (fewer than #SM/2 256-row items,
+// run as split-KV CTAs) is a programmatic dependent launch that backfills SMs as the persistent CTAs leave.
 #include "ief_common.cuh"
 #include "ptx_sm100.cuh"
 #include "attn_tc_host.cuh"
