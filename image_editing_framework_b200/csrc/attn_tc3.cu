@@ -213,7 +213,7 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     b = (int)bb;
     h = (int)hh;
     qt = (int)(rem - hh * (uint32_t)a.nq_blocks);
-    return a.rows.active[b] != 0;
+    return ((a.active_mask >> bb) & 1ull) != 0;
   };
   const int n_local = PERSIST ? (a.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 1;
   if constexpr (!PERSIST) {
@@ -841,14 +841,17 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma nounroll
       for (int e = 0; e < (NOMAX ? 2 : 1) * n_local; ++e) {
         bool exact;
+#if IEF_TC3_TRACE
+        const long long t_top = clock64();
+#endif
         int it = next_entry(e, exact);
         if (it == -2) break;
         if (it < 0 || !set_item(it)) continue;
         item_setup();
         l = 0.f;
 #if IEF_TC3_TRACE
-        long long* trk = cta_trace && row == 0 && half == 0 && k < 16 ? a.dbg + 1600 + (k * 2 + t) * 4 : nullptr;  // item start | loop end | epilogue end
-        if (trk) trk[0] = clock64();
+        long long* trk = cta_trace && row == 0 && half == 0 && k < 16 ? a.dbg + 1600 + (k * 2 + t) * 4 : nullptr;  // item start | loop end | epilogue end | loop top
+        if (trk) { trk[0] = clock64(); trk[3] = t_top; }
 #endif
         if constexpr (NOMAX) {
           if (!exact) {
@@ -941,6 +944,8 @@ int launch_tc3s(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap&
   // ceil(2^32 / divisor): floor(lin * rcp / 2^32) == lin / divisor for every lin < 2^32 / divisor
   const uint64_t div_h = (uint64_t)nq_blocks * (uint64_t)a.H, last = (uint64_t)first + (uint64_t)count;
   IEF_REQUIRE(last * div_h < (1ull << 32), IEF_ERR_UNSUPPORTED, "tcgen05 attention: %llu work items exceed the kernel's index arithmetic", (unsigned long long)last);
+  a.active_mask = 0;
+  for (int i = 0; i < a.B && i < 64; ++i) a.active_mask |= (uint64_t)(a.rows.active[i] != 0) << i;
   a.rcp_nq = ((1ull << 32) + (uint64_t)nq_blocks - 1) / (uint64_t)nq_blocks;
   a.rcp_nq_h = ((1ull << 32) + div_h - 1) / div_h;
   // Persistent form (one CTA per SM walks count / #SM items): 256-row flavour with more items than SMs and an even number of key

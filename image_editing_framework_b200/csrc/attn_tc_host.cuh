@@ -22,6 +22,7 @@ struct TcArgs {
   int32_t work_offset;  // attn_tc3: first linear work item (q block + nq_blocks * (head + H * row)) of this launch
   int32_t nq_blocks;    // attn_tc3: query blocks per (row, head) in this launch's flavour
   uint64_t rcp_nq, rcp_nq_h;  // attn_tc3: ceil(2^32 / nq_blocks), ceil(2^32 / (nq_blocks * H)): work item -> (q block, head, row) without integer division
+  uint64_t active_mask; // attn_tc3: bit b = rows.active[b] (a scalar instead of an indexed constant-bank load between two items)
   int32_t pdl;          // attn_tc3: launched as a programmatic dependent of the previous attn_tc3 launch (the remainder of a hybrid call)
   int32_t n_items;      // attn_tc3: work items of this launch (a persistent CTA takes blockIdx.x, blockIdx.x + gridDim.x, ...)
   float* lse_out;         // attn_tc2 / attn_tc3: row log-sum-exp in log2 units, [B][H][Nq] (for the stored-maps sweep), or null

@@ -52,6 +52,7 @@ if int(it[0, 0, 0]) != 0:
         row_ = []
         for s_ in range(2):
             a0, a1, a2 = (int(x) - int(c[0]) for x in it[k_, s_, :3])
+            top = int(it[k_, s_, 3]) - int(c[0])   # top of the item loop (before the item decode)
             nxt = int(it[k_ + 1, s_, 0]) - int(c[0]) if k_ + 1 < 16 and int(it[k_ + 1, s_, 0]) != 0 else None
-            row_.append(f"t{s_}: {a0:7d} {a1:7d} {a2:7d} (loop {a1 - a0}, epilogue {a2 - a1}" + (f", to next start {nxt - a2}, item {nxt - a0})" if nxt is not None else ")"))
+            row_.append(f"t{s_}: {a0:7d} {a1:7d} {a2:7d} (decode {a0 - top}, loop {a1 - a0}, epilogue {a2 - a1}" + (f", to next start {nxt - a2}, item {nxt - a0})" if nxt is not None else ")"))
         print(f"  item {k_:2d} | " + " | ".join(row_))
