@@ -62,7 +62,9 @@ constexpr int kRegsLow = 32, kRegsHigh = 112;  // pool = 640 threads x 96 regs a
 #ifndef IEF_TC3_STAGES
 #define IEF_TC3_STAGES 3
 #endif
-constexpr int ST = IEF_TC3_STAGES;   // K / V ring depth (4: no gain, profiles/r02 notes)
+#ifndef IEF_TC3_STAGES_PAIR
+#define IEF_TC3_STAGES_PAIR IEF_TC3_STAGES  // ring depth of the 256-row flavour (one K + one V tile per stage: 4 stages fit, the split flavour's 3 x 4 tiles do not)
+#endif
 constexpr int kTile = kTcChunkBytes;           // 16 KiB: one [128 x 64ch] box (head_dim <= 64)
 constexpr int kSmemOnes = 2 * 1024;            // [16 x 64] tile of 1.0 (K-major, SWIZZLE_128B footprint): B operand of the row-sum MMA
 constexpr int kSmemXchg = 8 * 1024;            // floats: row-max exchange [2 parities][2 streams][2 halves][128] | row sums [2][2][128] | split merge [2][128]
@@ -178,7 +180,8 @@ template <bool V> struct BoolTag { static constexpr bool value = V; };
 template <bool SPLIT> struct Cfg3 {
   static constexpr int kQTiles = SPLIT ? 1 : 2;
   static constexpr int kRingTiles = SPLIT ? 2 : 1;                       // K (and V) tiles per ring stage
-  static constexpr int kSmemData = kTile * (kQTiles + 2 * ST * kRingTiles);
+  static constexpr int kStages = SPLIT ? IEF_TC3_STAGES : IEF_TC3_STAGES_PAIR;  // K / V ring depth (4: no gain, profiles/r02 notes)
+  static constexpr int kSmemData = kTile * (kQTiles + 2 * kStages * kRingTiles);
   static constexpr int kSmemBytes = kSmemData + kSmemOnes + kSmemXchg + 1024 + 256;
 };
 
@@ -194,6 +197,7 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   using E = ElemT<DTYPE>;
   using Cfg = Cfg3<SPLIT>;
   constexpr int RT = Cfg::kRingTiles;
+  constexpr int ST = Cfg::kStages;
   constexpr bool SKIP = MAXMODE == 1, NOMAX = MAXMODE == 2;
   static_assert(!(NOMAX && BIAS), "the unshifted loop has no key-bias form");
   // persistent form: 256-row flavour only (the split flavour stages its merge in the K ring), not for the key-norm variant (its
