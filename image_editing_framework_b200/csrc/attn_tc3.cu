@@ -948,6 +948,7 @@ int launch_tc3s(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap&
   // ceil(2^32 / divisor): floor(lin * rcp / 2^32) == lin / divisor for every lin < 2^32 / divisor
   const uint64_t div_h = (uint64_t)nq_blocks * (uint64_t)a.H, last = (uint64_t)first + (uint64_t)count;
   IEF_REQUIRE(last * div_h < (1ull << 32), IEF_ERR_UNSUPPORTED, "tcgen05 attention: %llu work items exceed the kernel's index arithmetic", (unsigned long long)last);
+  static_assert(IEF_MAX_ROWS <= 64, "TcArgs::active_mask holds one bit per batch row");
   a.active_mask = 0;
   for (int i = 0; i < a.B && i < 64; ++i) a.active_mask |= (uint64_t)(a.rows.active[i] != 0) << i;
   a.rcp_nq = ((1ull << 32) + (uint64_t)nq_blocks - 1) / (uint64_t)nq_blocks;
