@@ -20,7 +20,7 @@
 #include <stdlib.h>
 
 bool ief_cross_tc_supported(const ief_cross_params* p);
-int ief_cross_tc_launch(const ief_cross_params* p, cudaStream_t st, const int32_t* rows = nullptr, int n_rows = 0);
+int ief_cross_tc_launch(const ief_cross_params* p, cudaStream_t st, const int32_t* rows = nullptr, int n_rows = 0, int pdl = 0);
 int ief_cross_tc_edit_launch(const ief_cross_params* p, const int32_t* rows, int n_rows, cudaStream_t st);
 
 using namespace mmau;
@@ -359,18 +359,22 @@ extern "C" int ief_cross_attn_edit_fwd(const ief_cross_params* p, void* stream) 
     }
     if (edit_on) {
       g_last_cross_impl = "tcgen05-edit";
-      // The call's plain rows ride in the edit kernel's launch, after the edited ones (longest CTAs first): a second, serialised launch
-      // of the leaner plain kernel costs more than it saves (N=4096,d=40: 31.7 -> 28.7 us; N=1024,d=80: 23.6 -> 18.5; N=256,d=160:
-      // 23.5 -> 14.4). IEF_CROSS_TC_ONE_LAUNCH=0 restores the two launches (A/B).
+      // Where do the call's plain rows run? (a) in the edit kernel's launch, after the edited ones (longest CTAs first), or (b) on the
+      // leaner plain kernel (128 TMEM columns: four CTAs per SM instead of two) in a second launch that is a PROGRAMMATIC DEPENDENT of
+      // the edit launch: disjoint rows, same inputs, so the two grids run side by side. Measured, P2P replace at B=4 (profiles/
+      // r02_cross_launch_modes.txt): N=4096,d=40  (a) 29.7 us  (b) 25.6;  N=1024,d=80  19.4 / 17.6;  N=256,d=160  15.3 / 15.4;
+      // with stored maps N=1024  23.6 / 25.6 — and a plain, serialised second launch is the slowest everywhere (33.7 / 23.6 / 23.5).
+      // Hence (b) for >= 1024 queries without a map output, (a) otherwise. IEF_CROSS_TC_ONE_LAUNCH=1|2|0 forces (a) / (b) / serialised.
       static int one = -1;
-      if (one < 0) { const char* e = getenv("IEF_CROSS_TC_ONE_LAUNCH"); one = (e && e[0] == '0') ? 0 : 1; }
-      if (one) {
+      if (one < 0) { const char* e = getenv("IEF_CROSS_TC_ONE_LAUNCH"); one = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : -1; }
+      const int how = one >= 0 ? one : ((p->probs_out == nullptr && p->Nq >= 1024 && np > 0) ? 2 : 1);
+      if (how == 1) {
         for (int i = 0; i < np; ++i) special[ns + i] = plain[i];
         return ief_cross_tc_edit_launch(p, special, ns + np, st);
       }
       int rc = ief_cross_tc_edit_launch(p, special, ns, st);
       if (rc != IEF_OK || np == 0) return rc;
-      return ief_cross_tc_launch(p, st, plain, np);
+      return ief_cross_tc_launch(p, st, plain, np, how == 2 ? 1 : 0);
     }
   }
   g_last_cross_impl = "mma";

@@ -32,6 +32,7 @@ struct CrossTcArgs {
   float scale_log2;
   int32_t perm_q[3], perm_k[3], perm_v[3];
   int32_t row[IEF_MAX_ROWS];   // blockIdx.z -> batch row (a call may hand its edited / stored rows to cross_tc_edit.cu)
+  int32_t pdl;                 // launched as a programmatic dependent of the edit kernel's launch of the same call
 };
 
 template <int DCH> constexpr int cross_tc_smem() { return DCH * (2 * kQChunk + 2 * kKVChunk) + 1024 + 128; }
@@ -42,6 +43,7 @@ cross_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 const __grid_constant__ CrossTcArgs a) {
   using E = ElemT<DTYPE>;
   constexpr int kTmemCols = TCOLS;   // 128 when 80 + dv <= 128 (head_dim <= 48), else 256
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // nothing of this grid is consumed by a dependent launch
   const int b = a.row[blockIdx.z], h = blockIdx.y;
   const int nqt = (a.Nq + kBM - 1) / kBM;
   const int qt0 = blockIdx.x * a.tiles_per_cta, ntile = min(a.tiles_per_cta, nqt - qt0);
@@ -197,6 +199,7 @@ cross_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     }
   }
+  if (a.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");  // a dependent launch must not complete before the launch it depends on
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -209,7 +212,21 @@ template <int DTYPE, int DCH, int TCOLS>
 int launch_cross_tc(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CrossTcArgs& a, dim3 grid, cudaStream_t st) {
   auto kern = cross_tc_kernel<DTYPE, DCH, TCOLS>;
   IEF_CONFIG_SMEM(kern, cross_tc_smem<DCH>());
-  kern<<<grid, kThreads, cross_tc_smem<DCH>(), st>>>(mq, mk, mv, a);
+  if (a.pdl) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = cross_tc_smem<DCH>();
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    IEF_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, mq, mk, mv, a));
+  } else {
+    kern<<<grid, kThreads, cross_tc_smem<DCH>(), st>>>(mq, mk, mv, a);
+  }
   IEF_LAUNCH_OK("cross_tc_kernel");
   return IEF_OK;
 }
@@ -224,8 +241,9 @@ bool ief_cross_tc_supported(const ief_cross_params* p) {
   return on && p->Nk <= kNK && p->d % 8 == 0 && p->d >= 8 && p->d <= 160 && p->Nq >= kBM && (p->dtype == IEF_BF16 || p->dtype == IEF_F16);
 }
 
-int ief_cross_tc_launch(const ief_cross_params* p, cudaStream_t st, const int32_t* rows, int n_rows) {
+int ief_cross_tc_launch(const ief_cross_params* p, cudaStream_t st, const int32_t* rows, int n_rows, int pdl) {
   CrossTcArgs a;
+  a.pdl = pdl;
   const int nb = rows ? n_rows : p->B;
   for (int i = 0; i < IEF_MAX_ROWS; ++i) a.row[i] = i < nb ? (rows ? rows[i] : i) : 0;
   a.o = p->o.ptr; a.o_sb = p->o.stride_b; a.o_sn = p->o.stride_n; a.o_sh = p->o.stride_h;

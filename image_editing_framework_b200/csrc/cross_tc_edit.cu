@@ -78,6 +78,7 @@ template <int DTYPE, int DCH, int TCOLS, bool EDIT, bool STORE>
 __global__ void __launch_bounds__(kThreads)
 cross_tc_edit_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                      const __grid_constant__ CrossTcEditArgs a) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // nothing of this grid is consumed by a dependent launch (cross_attn.cu)
   using E = ElemT<DTYPE>;
   constexpr int OFF_B = kNK, OFF_O = EDIT ? 2 * kNK : kNK;
   const int zi = blockIdx.z, b = a.row[zi], h = blockIdx.y, qt = blockIdx.x;

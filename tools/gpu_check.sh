@@ -20,6 +20,8 @@ run cross "cross_attention"
 IEF_CROSS_TC=0 run cross_mma_only "cross_attention"
 IEF_CROSS_TC_EDIT=0 run cross_edit_on_mma "cross_attention"
 IEF_CROSS_TC_ONE_LAUNCH=0 run cross_edit_two_launches "cross_attention"
+IEF_CROSS_TC_ONE_LAUNCH=1 run cross_edit_one_launch "cross_attention"
+IEF_CROSS_TC_ONE_LAUNCH=2 run cross_edit_dependent_launch "cross_attention"
 run masked "key_bias or mask_blend"
 IEF_PROBS_VIA_LSE=0 run probs_two_sweep "probs_out"
 run backward "cross_attention_backward"
